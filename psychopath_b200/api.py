@@ -1,0 +1,272 @@
+"""Host-side mirror of the reference's interface to the render core, bound to the CUDA library
+through the C ABI (include/psy_cuda.h).
+
+  Scene      <- what `parse_scene` returns inside `Renderer` (src/parse/psy.rs:95-200): the built scene
+  Renderer   <- `Renderer { output_file, resolution, spp, seed, scene }` and `Renderer::render(
+                max_samples_per_bucket, crop, thread_count, do_blender_output) -> (Image, RenderStats)`
+                (src/renderer.rs:32-38,76-191)
+  Tracer     <- `Tracer::from_assembly` / `Tracer::trace(&mut RayBatch) -> &[SurfaceIntersection]`
+                (src/tracer.rs:22-37)
+
+There is no CPU path here: if libpsy_cuda.so is missing or no GPU is visible the constructors raise.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+_host = None
+_cuda = None
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        _host = abi.load_host()
+    return _host
+
+
+def cuda_lib():
+    global _cuda
+    if _cuda is None:
+        _cuda = abi.load_cuda()
+    return _cuda
+
+
+class PsyError(RuntimeError):
+    pass
+
+
+class Scene:
+    """A parsed and built scene living in host memory (flat PsySceneDesc)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self.desc = host_lib().psyh_scene_desc(handle)
+
+    def __del__(self):
+        try:
+            if self._h:
+                host_lib().psyh_scene_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def _check(rc):
+        if rc != 0:
+            raise PsyError(host_lib().psyh_last_error().decode())
+
+    @classmethod
+    def from_psy_file(cls, path, index=0):
+        h = C.c_void_p()
+        cls._check(host_lib().psyh_load_psy_file(str(path).encode(), index, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_psy_string(cls, text, index=0):
+        h = C.c_void_p()
+        cls._check(host_lib().psyh_load_psy_string(text.encode(), index, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def synth_displaced_grid(cls, quads_per_side, n_vert_keys=4, n_xform_keys=4, res=(1920, 1080), spp=128, seed=3):
+        h = C.c_void_p()
+        cls._check(host_lib().psyh_synth_displaced_grid(quads_per_side, n_vert_keys, n_xform_keys, res[0], res[1], spp,
+                                                        seed, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def synth_instanced(cls, asset_quads=500, n_assets=4, n_clusters=100, inst_per_cluster=10, lights_per_cluster=10,
+                        cluster_xform_keys=2, res=(1920, 1080), spp=64, seed=4):
+        h = C.c_void_p()
+        cls._check(host_lib().psyh_synth_instanced(asset_quads, n_assets, n_clusters, inst_per_cluster,
+                                                   lights_per_cluster, cluster_xform_keys, res[0], res[1], spp, seed,
+                                                   C.byref(h)))
+        return cls(h)
+
+    def set_render(self, res=None, spp=0, seed=None):
+        d = self.desc.contents
+        host_lib().psyh_scene_set_render(self._h, res[0] if res else 0, res[1] if res else 0, spp,
+                                         d.seed if seed is None else seed)
+
+    @property
+    def resolution(self):
+        d = self.desc.contents
+        return (d.res_x, d.res_y)
+
+    @property
+    def spp(self):
+        return self.desc.contents.spp
+
+    @property
+    def seed(self):
+        return self.desc.contents.seed
+
+    @property
+    def output_file(self):
+        return host_lib().psyh_output_path(self._h).decode()
+
+    @property
+    def build_seconds(self):
+        return host_lib().psyh_build_seconds(self._h)
+
+    def host_bytes(self):
+        """Bytes of scene data the upload copies host->device."""
+        d = self.desc.contents
+        return (d.n_nodes * 128 + d.n_motion_bounds * 96 + d.n_tris * 16 + d.n_vert_keys * 24 + d.n_instances * 24 +
+                d.n_xforms * 48 + d.n_light_nodes * 24 + d.n_lt_bounds * 24)
+
+
+_ctx = {}
+
+
+def _context(device):
+    lib = cuda_lib()
+    if device not in _ctx:
+        ctx = C.c_void_p()
+        ids = (C.c_int * 1)(device)
+        rc = lib.psy_init(ids, 1, C.byref(ctx))
+        if rc != 0:
+            raise PsyError(f"psy_init failed ({rc}): {lib.psy_last_error().decode()}")
+        _ctx[device] = ctx
+    return _ctx[device]
+
+
+def stats_dict(st):
+    return {k: getattr(st, k) for k, _ in abi.PsyStats._fields_}
+
+
+class DeviceScene:
+    """The scene uploaded to one GPU (PsyScene*)."""
+
+    def __init__(self, scene, device=0):
+        self.scene = scene
+        self.lib = cuda_lib()
+        self.ctx = _context(device)
+        self.device = device
+        self._s = C.c_void_p()
+        rc = self.lib.psy_scene_create(self.ctx, scene.desc, C.byref(self._s))
+        if rc != 0:
+            raise PsyError(f"psy_scene_create failed ({rc}): {self.lib.psy_last_error().decode()}")
+
+    def close(self):
+        if self._s:
+            self.lib.psy_scene_destroy(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise PsyError(f"{what} failed ({rc}): {self.lib.psy_last_error().decode()}")
+
+
+class Tracer(DeviceScene):
+    """Tracer::trace over a batch of probe rays."""
+
+    def trace(self, rays, want_geo=False):
+        rays = np.ascontiguousarray(rays, dtype=abi.RAY_DTYPE)
+        hits = np.zeros(len(rays), dtype=abi.HIT_DTYPE)
+        geo = np.zeros(len(rays), dtype=abi.GEO_DTYPE) if want_geo else None
+        self._check(self.lib.psy_trace_rays(self._s, rays.ctypes.data, len(rays), hits.ctypes.data,
+                                            geo.ctypes.data if want_geo else None), "psy_trace_rays")
+        return (hits, geo) if want_geo else hits
+
+
+class Renderer(Tracer):
+    """Renderer::render and the per-bucket body of render_job."""
+
+    @property
+    def resolution(self):
+        return self.scene.resolution
+
+    @property
+    def spp(self):
+        return self.scene.spp
+
+    @property
+    def seed(self):
+        return self.scene.seed
+
+    @property
+    def output_file(self):
+        return self.scene.output_file
+
+    def _params(self, max_samples_per_bucket, crop, spp, seed, counters, resident):
+        p = abi.PsyRenderParams()
+        if crop is not None:
+            p.crop_enabled = 1
+            p.crop_x1, p.crop_y1, p.crop_x2, p.crop_y2 = [int(c) for c in crop]
+        p.spp = int(spp or 0)
+        if seed is not None:
+            p.seed_override_enabled = 1
+            p.seed = int(seed)
+        p.max_samples_per_bucket = int(max_samples_per_bucket or 0)
+        p.collect_counters = 1 if counters else 0
+        p.device_resident_only = 1 if resident else 0
+        return p
+
+    def render(self, max_samples_per_bucket=0, crop=None, thread_count=None, do_blender_output=False, spp=None,
+               seed=None, counters=False, on_bucket=None, device_resident_only=False):
+        """Returns (image, stats): image is float32 (res_y, res_x, 3) XYZ, row 0 = top (None when
+        device_resident_only).  thread_count is accepted for signature parity and ignored."""
+        p = self._params(max_samples_per_bucket, crop, spp, seed, counters, device_resident_only)
+        rx, ry = self.resolution
+        img = None if device_resident_only else np.zeros((ry, rx, 3), dtype=np.float32)
+        st = abi.PsyStats()
+        cb = None
+        if on_bucket is not None:
+            def _cb(user, x0, y0, x1, y1, ptr):
+                n = (x1 - x0) * (y1 - y0) * 3
+                on_bucket(x0, y0, x1, y1, np.ctypeslib.as_array(ptr, shape=(n,)).reshape(y1 - y0, x1 - x0, 3).copy())
+            cb = abi.BUCKET_CB(_cb)
+        self._check(self.lib.psy_render_image(self._s, C.byref(p), img.ctypes.data if img is not None else None,
+                                              C.byref(st), C.cast(cb, C.c_void_p) if cb else None, None),
+                    "psy_render_image")
+        return img, stats_dict(st)
+
+    def render_shard(self, rank, world, max_samples_per_bucket=0, spp=None, seed=None):
+        p = self._params(max_samples_per_bucket, None, spp, seed, False, True)
+        st = abi.PsyStats()
+        self._check(self.lib.psy_render_image_shard(self._s, C.byref(p), rank, world, C.byref(st)),
+                    "psy_render_image_shard")
+        return stats_dict(st)
+
+    def device_image(self):
+        ptr = C.c_void_p()
+        n = C.c_size_t()
+        self._check(self.lib.psy_device_image(self._s, C.byref(ptr), C.byref(n)), "psy_device_image")
+        return ptr.value, n.value
+
+    def fetch_image(self):
+        rx, ry = self.resolution
+        img = np.zeros((ry, rx, 3), dtype=np.float32)
+        self._check(self.lib.psy_fetch_image(self._s, img.ctypes.data), "psy_fetch_image")
+        return img
+
+    def render_bucket(self, x, y, w, h, spp=None, seed=None):
+        xyz = np.zeros((h, w, 3), dtype=np.float32)
+        st = abi.PsyStats()
+        self._check(self.lib.psy_render_bucket(self._s, x, y, w, h, spp or self.spp, self.seed if seed is None else seed,
+                                               xyz.ctypes.data, C.byref(st)), "psy_render_bucket")
+        return xyz, stats_dict(st)
+
+    def render_bucket_samples(self, x, y, w, h, spp=None, seed=None):
+        spp = spp or self.spp
+        out = np.zeros((h, w, spp, 4), dtype=np.float32)
+        st = abi.PsyStats()
+        self._check(self.lib.psy_render_bucket_samples(self._s, x, y, w, h, spp, self.seed if seed is None else seed,
+                                                       out.ctypes.data, C.byref(st)), "psy_render_bucket_samples")
+        return out, stats_dict(st)
+
+    def last_trace_timing(self):
+        ms = C.c_double()
+        n = C.c_uint64()
+        self._check(self.lib.psy_last_trace_timing(self._s, C.byref(ms), C.byref(n)), "psy_last_trace_timing")
+        return ms.value, n.value

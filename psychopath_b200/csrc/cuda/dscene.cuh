@@ -1,0 +1,82 @@
+// dscene.cuh — the scene as it lives in HBM (DESIGN.md "Data layout").
+#pragma once
+#include "../../../include/psy_cuda.h"
+#include "dmath.cuh"
+
+namespace psyd {
+
+// One expanded instance path (a chain of instances from the root assembly to this instance).
+// Paths are numbered breadth-first: children of assembly-instance path p are child_base + i.
+struct DPath {
+    uint32_t inst;        // global instance index
+    uint32_t child_base;  // first child path if the instance is an assembly, else PSY_NONE
+    uint32_t xf_base;     // composed world->local keys in path_xforms (units of transforms)
+    uint32_t xf_count;    // 0 = no transform anywhere on the chain (space.is_empty())
+};
+
+struct DMesh {
+    uint32_t root, tri_base, tri_count, n_keys;
+    uint32_t tv_base;    // first float4 of this mesh's gathered triangle vertices
+    uint32_t vert_base;  // vertex-key base for the normals
+    uint32_t has_normals, pad;
+};
+
+struct DScene {
+    // acceleration structures
+    const uint4* nodes;          // PsyBvh4Node as 8 x 16 B
+    const float4* motion_bounds; // PsyBBox4 as 6 x float4 per key
+    // geometry: per triangle (leaf order) 3*k float4: [v0 keys][v1 keys][v2 keys]; v0-key0 .w = original index
+    const float4* tri_verts;
+    const uint4* tris;     // (v0, v2, v1, original index)
+    const float4* normals; // per vertex-key
+    const DMesh* meshes;
+    const PsyLight* lights;
+    const float* light_shape;
+    const PsyColor* light_colors;
+    const PsyObject* objects;
+    const PsyShader* shaders;
+    const PsyAssembly* assemblies;
+    const PsyInstance* instances;
+    const PsyInstance* light_instances;
+    const uint32_t* light_inst_local;  // light instance -> index inside its assembly's instance list
+    const float4* xforms;       // instance transforms, 3 rows each
+    const PsyLightNode* light_nodes;
+    const PsyBBox* lt_bounds;
+    // instance paths
+    const DPath* paths;
+    const float4* path_xforms;  // composed keys, 3 rows each
+    const float4* path_inv;     // per path: inverse of the single composed key (valid when xf_count == 1)
+    uint32_t root_assembly;
+    uint32_t n_paths;
+    // camera
+    const float4* cam_xforms;
+    const float* cam_tfovs;
+    const float* cam_aperture;
+    const float* cam_focus;
+    uint32_t n_cam_xforms, n_cam_tfovs, n_cam_aperture, n_cam_focus;
+    // world
+    PsyColor background;
+    const PsyDistantLight* distant_lights;
+    const float* world_floats;
+    uint32_t n_distant_lights;
+    float world_light_energy_sum;  // fold of approximate_energy over world lights
+    // spectral tables
+    const float* meng_spectra;  // [186][95]
+    uint32_t res_x, res_y;
+};
+
+// Hit record written by the trace kernel (32 B)
+struct HitRec {
+    uint32_t kind;  // PSY_HIT_*
+    float t;
+    uint32_t prim;  // triangle: global triangle index; rect light: 0/1
+    uint32_t path;
+    float b0, b1, b2;
+    uint32_t pad;
+};
+
+struct TraceCounters {
+    unsigned long long node_visits, tri_tests, instance_visits, motion_node_visits;
+};
+
+}  // namespace psyd

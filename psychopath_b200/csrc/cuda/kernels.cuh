@@ -1,0 +1,381 @@
+// kernels.cuh — the wavefront stages.  One path owns one slot of the SoA path pool; every wave
+// traces exactly one ray per live path (camera/bounce ray or shadow ray), like the reference's
+// wave loop (src/renderer.rs:279-297), and the live list is compacted with warp ballots.
+//
+//   k_generate  <- renderer.rs:241-275  (sampler, pixel filter, LightPath::new, Camera::generate_ray)
+//   k_trace     <- Tracer::trace        (src/tracer.rs:34-37; dtrace.cuh)
+//   k_shade     <- LightPath::next      (renderer.rs:449-691)
+//   k_film      <- renderer.rs:299-310  (XYZ::from_spectral_sample / spp, summed per pixel)
+#pragma once
+#include <math_constants.h>
+
+#include "dshade.cuh"
+
+namespace psyd {
+
+// flags word of a path
+constexpr uint32_t F_OCCLUSION = 1u;       // the ray now in the slot is a shadow ray
+constexpr uint32_t F_EVENT_SHIFT = 1;      // 0 camera, 1 bounce, 2 shadow
+constexpr uint32_t F_EVENT_MASK = 3u << 1;
+constexpr uint32_t F_BOUNCE_SHIFT = 3;
+constexpr uint32_t F_BOUNCE_MASK = 3u << 3;
+constexpr uint32_t F_HAS_NEXT = 1u << 5;
+constexpr uint32_t EV_CAMERA = 0, EV_BOUNCE = 1, EV_SHADOW = 2;
+
+struct PathPool {
+    float4* ray_o;  // orig.xyz, time
+    float4* ray_d;  // dir.xyz, max_t
+    uint32_t* flags;
+    uint32_t* sseed;
+    float* wavelength;
+    float* closure_pdf;
+    float4* nb_o;  // next bounce ray origin
+    float4* nb_d;  // next bounce ray direction
+    float4* next_atten;
+    float4* light_atten;
+    float4* pending;
+    float4* color;
+    HitRec* hits;
+};
+
+struct Bucket {
+    uint32_t x, y, w, h, spp, seed;
+};
+
+// Camera::generate_ray (camera.rs:74-102)
+PSY_DEV void camera_ray(const DScene& S, float x, float y, float time, float u, float v, V3& orig, V3& dir) {
+    Xf transform = lerp_slice_xf(S.cam_xforms, S.n_cam_xforms, time);
+    float tfov = lerp_slice_f(S.cam_tfovs, S.n_cam_tfovs, time);
+    float aperture_radius = lerp_slice_f(S.cam_aperture, S.n_cam_aperture, time);
+    float focus_distance = lerp_slice_f(S.cam_focus, S.n_cam_focus, time);
+    float cu, cv;
+    square_to_circle((u * 2.0f) - 1.0f, (v * 2.0f) - 1.0f, cu, cv);
+    V3 o = mk3(aperture_radius * cu, aperture_radius * cv, 0.0f);
+    V3 d = normalized(mk3((x * tfov) - (o.x / focus_distance), (y * tfov) - (o.y / focus_distance), 1.0f));
+    orig = xf_point(transform, o);
+    dir = xf_vector(transform, d);
+}
+
+__global__ void __launch_bounds__(256) k_generate(DScene S, PathPool P, Bucket b, uint32_t n, uint32_t* active,
+                                                  uint32_t* count0) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *count0 = n;
+    if (i >= n) return;
+    uint32_t q = i / b.spp, si = i - q * b.spp;
+    uint32_t px = b.x + (q % b.w), py = b.y + (q / b.w);
+    float s0[4], s1[4];
+    get_sample_4d(si, 0, px, py, b.seed, s0);
+    get_sample_4d(si, 1, px, py, b.seed, s1);
+    float cmpx = 1.0f / (float)S.res_x, cmpy = 1.0f / (float)S.res_y;
+    float min_y = -((float)S.res_y / (float)S.res_x), max_y = (float)S.res_y / (float)S.res_x;
+    float x_extent = 1.0f - -1.0f, y_extent = max_y - min_y;
+    float filter_x = probit(s0[3], 2.0f / 6.0f) + 0.5f;
+    float filter_y = probit(s1[0], 2.0f / 6.0f) + 0.5f;
+    float samp_x = (filter_x + (float)px) * cmpx;
+    float samp_y = (filter_y + (float)py) * cmpy;
+    float img_x = (samp_x - 0.5f) * x_extent;
+    float img_y = (0.5f - samp_y) * y_extent;
+    float wl = map_0_1_to_wavelength(golden_ratio_sample(si, hash_u32((px << 16) ^ py, b.seed)));
+    V3 o, d;
+    camera_ray(S, img_x, img_y, s0[0], s0[1], s0[2], o, d);
+    P.ray_o[i] = make_float4(o.x, o.y, o.z, s0[0]);
+    P.ray_d[i] = make_float4(d.x, d.y, d.z, CUDART_INF_F);
+    P.flags[i] = (EV_CAMERA << F_EVENT_SHIFT);
+    P.sseed[i] = b.seed ^ 0x40d4682bu;
+    P.wavelength[i] = wl;
+    P.closure_pdf[i] = 1.0f;
+    P.next_atten[i] = make_float4(1, 1, 1, 1);
+    P.light_atten[i] = make_float4(1, 1, 1, 1);
+    P.pending[i] = make_float4(0, 0, 0, 0);
+    P.color[i] = make_float4(0, 0, 0, 0);
+    active[i] = i;
+}
+
+// Persistent trace kernel: warps fetch 32 rays at a time from a global counter.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace(DScene S, PathPool P, const uint32_t* __restrict__ active,
+                                               const uint32_t* __restrict__ count, uint32_t* fetch,
+                                               TraceCounters* counters) {
+    const uint32_t n = *count;
+    const uint32_t lane = threadIdx.x & 31u;
+    TraceCounters cnt;
+    cnt.node_visits = cnt.tri_tests = cnt.instance_visits = cnt.motion_node_visits = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(fetch, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + lane;
+        if (i < n) {
+            uint32_t slot = active[i];
+            float4 ro = P.ray_o[slot], rd = P.ray_d[slot];
+            RayIn ray;
+            ray.orig = mk3(ro.x, ro.y, ro.z);
+            ray.dir = mk3(rd.x, rd.y, rd.z);
+            ray.time = ro.w;
+            ray.max_t = rd.w;
+            ray.occlusion = (P.flags[slot] & F_OCCLUSION) != 0u;
+            HitRec hit;
+            trace_ray<COUNT>(S, ray, hit, cnt);
+            uint4* hp = reinterpret_cast<uint4*>(P.hits + slot);
+            hp[0] = make_uint4(hit.kind, __float_as_uint(hit.t), hit.prim, hit.path);
+            hp[1] = make_uint4(__float_as_uint(hit.b0), __float_as_uint(hit.b1), __float_as_uint(hit.b2), 0u);
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&counters->node_visits, cnt.node_visits);
+        atomicAdd(&counters->tri_tests, cnt.tri_tests);
+        atomicAdd(&counters->instance_visits, cnt.instance_visits);
+        atomicAdd(&counters->motion_node_visits, cnt.motion_node_visits);
+    }
+}
+
+// Probe rays: trace + finalise into the ABI's PsyHit / PsyHitGeo (psy_trace_rays)
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_probe(DScene S, const PsyRay* __restrict__ rays, uint32_t n, PsyHit* hits,
+                                                     PsyHitGeo* geo, TraceCounters* counters) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    TraceCounters cnt;
+    cnt.node_visits = cnt.tri_tests = cnt.instance_visits = cnt.motion_node_visits = 0;
+    if (i < n) {
+        PsyRay r = rays[i];
+        RayIn ray;
+        ray.orig = mk3(r.orig[0], r.orig[1], r.orig[2]);
+        ray.dir = mk3(r.dir[0], r.dir[1], r.dir[2]);
+        ray.time = r.time;
+        ray.max_t = r.max_t;
+        ray.occlusion = (r.flags & PSY_RAY_OCCLUSION) != 0u;
+        HitRec h;
+        trace_ray<COUNT>(S, ray, h, cnt);
+        PsyHit o;
+        o.kind = h.kind;
+        o.t = h.t;
+        o.prim_id = 0;
+        o.inst_id = 0;
+        o.path_id = 0;
+        o.b0 = h.b0, o.b1 = h.b1, o.b2 = h.b2;
+        bool is_hit = h.kind == PSY_HIT_TRIANGLE || h.kind == PSY_HIT_SPHERE_LIGHT || h.kind == PSY_HIT_RECT_LIGHT;
+        if (is_hit) {
+            o.path_id = h.path;
+            o.inst_id = S.instances[S.paths[h.path].inst].id;
+            o.prim_id = h.kind == PSY_HIT_TRIANGLE ? S.tris[h.prim].w : h.prim;
+        }
+        hits[i] = o;
+        if (geo) {
+            PsyHitGeo g;
+            g.pos[0] = g.pos[1] = g.pos[2] = 0.0f;
+            g.pos_err = 0.0f;
+            g.nor[0] = g.nor[1] = g.nor[2] = 0.0f;
+            g.sample_pdf = 0.0f;
+            g.nor_g[0] = g.nor_g[1] = g.nor_g[2] = 0.0f;
+            g.closure_kind = 0;
+            if (is_hit) {
+                Isect is;
+                finalize_hit(S, h, ray.orig, ray.dir, ray.time, is);
+                g.pos[0] = is.pos.x, g.pos[1] = is.pos.y, g.pos[2] = is.pos.z;
+                g.pos_err = is.pos_err;
+                g.nor[0] = is.nor.x, g.nor[1] = is.nor.y, g.nor[2] = is.nor.z;
+                g.sample_pdf = is.sample_pdf;
+                g.nor_g[0] = is.nor_g.x, g.nor_g[1] = is.nor_g.y, g.nor_g[2] = is.nor_g.z;
+                g.closure_kind = is.closure.kind;
+            }
+            geo[i] = g;
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&counters->node_visits, cnt.node_visits);
+        atomicAdd(&counters->tri_tests, cnt.tri_tests);
+        atomicAdd(&counters->instance_visits, cnt.instance_visits);
+        atomicAdd(&counters->motion_node_visits, cnt.motion_node_visits);
+    }
+}
+
+// LightPath::next for one path; returns true when the path stays alive (a new ray was written).
+PSY_DEV bool path_next(const DScene& S, const PathPool& P, uint32_t slot, const Bucket& b) {
+    uint32_t flags = P.flags[slot];
+    uint32_t event = (flags & F_EVENT_MASK) >> F_EVENT_SHIFT;
+    const HitRec h = P.hits[slot];
+    float4 ro = P.ray_o[slot];
+    const float time = ro.w;
+    const float wl = P.wavelength[slot];
+
+    if (event == EV_SHADOW) {
+        // renderer.rs:673-689
+        if (h.kind == PSY_HIT_MISS) P.color[slot] = to_f4(from_f4(P.color[slot]) + from_f4(P.pending[slot]));
+        if (flags & F_HAS_NEXT) {
+            float4 o = P.nb_o[slot], d = P.nb_d[slot];
+            P.ray_o[slot] = make_float4(o.x, o.y, o.z, time);
+            P.ray_d[slot] = make_float4(d.x, d.y, d.z, CUDART_INF_F);
+            P.light_atten[slot] = to_f4(from_f4(P.light_atten[slot]) * from_f4(P.next_atten[slot]));
+            flags = (flags & ~(F_EVENT_MASK | F_OCCLUSION)) | (EV_BOUNCE << F_EVENT_SHIFT);
+            P.flags[slot] = flags;
+            return true;
+        }
+        return false;
+    }
+
+    float4 rd = P.ray_d[slot];
+    V3 orig = mk3(ro.x, ro.y, ro.z), dir = mk3(rd.x, rd.y, rd.z);
+    V4 light_attenuation = from_f4(P.light_atten[slot]);
+    float closure_sample_pdf = P.closure_pdf[slot];
+
+    bool is_hit = h.kind == PSY_HIT_TRIANGLE || h.kind == PSY_HIT_SPHERE_LIGHT || h.kind == PSY_HIT_RECT_LIGHT;
+    if (!is_hit) {
+        // background (renderer.rs:659-667)
+        V4 bg = color_to_spectral(S, S.background, wl);
+        P.color[slot] = to_f4(from_f4(P.color[slot]) + ((bg * light_attenuation) / closure_sample_pdf));
+        return false;
+    }
+    Isect is;
+    finalize_hit(S, h, orig, dir, time, is);
+
+    if (is.closure.kind == PSY_SHADER_EMIT) {
+        // renderer.rs:472-483
+        V4 c = color_to_spectral(S, is.closure.color, wl);
+        V4 col = from_f4(P.color[slot]);
+        if (event == EV_CAMERA) {
+            col = col + c;
+        } else {
+            float mis_pdf = power_heuristic(closure_sample_pdf, is.sample_pdf);
+            col = col + ((c * light_attenuation) / mis_pdf);
+        }
+        P.color[slot] = to_f4(col);
+        return false;
+    }
+    light_attenuation = light_attenuation / closure_sample_pdf;
+
+    // light sample (renderer.rs:488-596)
+    uint32_t sseed = P.sseed[slot];
+    uint32_t q = slot / b.spp, si = slot - q * b.spp;
+    uint32_t px = b.x + (q % b.w), py = b.y + (q / b.w);
+    sseed += 1u;
+    float s4[4];
+    get_sample_4d(si, 0, px, py, sseed, s4);
+    LightSample li;
+    sample_lights(S, s4[0], s4[1], s4[2], wl, time, is, li);
+    bool found_light = false;
+    if (!(li.kind == 0 || li.pdf <= 0.0f || li.selection_pdf <= 0.0f)) {
+        V4 attenuation;
+        float closure_pdf;
+        V3 so, sd;
+        float smax;
+        V3 ng = normalized(is.nor_g);
+        if (li.kind == 1) {
+            closure_evaluate(S, is.closure, dir, li.direction, is.nor, is.nor_g, wl, attenuation, closure_pdf);
+            so = robust_ray_origin(is.pos, is.pos_err, ng, li.direction);
+            sd = li.direction;
+            smax = CUDART_INF_F;
+        } else {
+            V3 ldir = li.pos - is.pos;
+            closure_evaluate(S, is.closure, dir, ldir, is.nor, is.nor_g, wl, attenuation, closure_pdf);
+            so = robust_ray_origin(is.pos, is.pos_err, ng, ldir);
+            V3 offset_end = robust_ray_origin(li.pos, li.err, normalized(li.nor), -ldir);
+            sd = offset_end - so;
+            smax = 1.0f;
+        }
+        if (!(max_element4(attenuation) <= 0.0f)) {
+            float light_mis_pdf = power_heuristic(li.pdf, closure_pdf);
+            V4 pend = ((li.color * attenuation) * light_attenuation) / (light_mis_pdf * li.selection_pdf);
+            P.pending[slot] = to_f4(pend);
+            P.ray_o[slot] = make_float4(so.x, so.y, so.z, time);
+            P.ray_d[slot] = make_float4(sd.x, sd.y, sd.z, smax);
+            found_light = true;
+        }
+    }
+
+    // bounce (renderer.rs:598-644)
+    bool do_bounce = false;
+    uint32_t bounce_count = (flags & F_BOUNCE_MASK) >> F_BOUNCE_SHIFT;
+    V3 nb_o = mk3(0, 0, 0), nb_d = mk3(0, 0, 0);
+    V4 next_atten = from_f4(P.next_atten[slot]);
+    if (bounce_count < 2u) {
+        bounce_count += 1u;
+        sseed += 1u;
+        float b4[4];
+        get_sample_4d(si, 0, px, py, sseed, b4);
+        V3 bdir;
+        V4 filter;
+        float pdf;
+        closure_sample(S, is.closure, is.incoming, is.nor, is.nor_g, b4[0], b4[1], wl, bdir, filter, pdf);
+        if ((pdf > 0.0f) && (max_element4(filter) > 0.0f)) {
+            next_atten = filter;
+            closure_sample_pdf = pdf;
+            nb_o = robust_ray_origin(is.pos, is.pos_err, normalized(is.nor_g), bdir);
+            nb_d = bdir;
+            flags |= F_HAS_NEXT;
+            do_bounce = true;
+            P.nb_o[slot] = make_float4(nb_o.x, nb_o.y, nb_o.z, 0.0f);
+            P.nb_d[slot] = make_float4(nb_d.x, nb_d.y, nb_d.z, 0.0f);
+            P.next_atten[slot] = to_f4(next_atten);
+        }
+    } else {
+        flags &= ~F_HAS_NEXT;
+    }
+    flags = (flags & ~F_BOUNCE_MASK) | (bounce_count << F_BOUNCE_SHIFT);
+    P.sseed[slot] = sseed;
+    P.closure_pdf[slot] = closure_sample_pdf;
+
+    if (found_light) {
+        flags = (flags & ~F_EVENT_MASK) | (EV_SHADOW << F_EVENT_SHIFT) | F_OCCLUSION;
+        P.flags[slot] = flags;
+        P.light_atten[slot] = to_f4(light_attenuation);
+        return true;
+    } else if (do_bounce) {
+        P.ray_o[slot] = make_float4(nb_o.x, nb_o.y, nb_o.z, time);
+        P.ray_d[slot] = make_float4(nb_d.x, nb_d.y, nb_d.z, CUDART_INF_F);
+        flags = (flags & ~(F_EVENT_MASK | F_OCCLUSION)) | (EV_BOUNCE << F_EVENT_SHIFT);
+        P.flags[slot] = flags;
+        P.light_atten[slot] = to_f4(light_attenuation * next_atten);
+        return true;
+    }
+    P.flags[slot] = flags;
+    P.light_atten[slot] = to_f4(light_attenuation);
+    return false;
+}
+
+__global__ void __launch_bounds__(128) k_shade(DScene S, PathPool P, Bucket b, const uint32_t* __restrict__ active_in,
+                                               const uint32_t* __restrict__ count_in, uint32_t* active_out,
+                                               uint32_t* count_out) {
+    const uint32_t n = *count_in;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+        uint32_t i = base + lane;
+        bool alive = false;
+        uint32_t slot = 0;
+        if (i < n) {
+            slot = active_in[i];
+            alive = path_next(S, P, slot, b);
+        }
+        // stream compaction: ballot + popc prefix + one atomic per warp (replaces the swap
+        // compaction of renderer.rs:286-295)
+        uint32_t mask = __ballot_sync(0xffffffffu, alive);
+        uint32_t warp_base = 0;
+        if (lane == 0 && mask) warp_base = atomicAdd(count_out, __popc(mask));
+        warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+        if (alive) active_out[warp_base + __popc(mask & ((1u << lane) - 1u))] = slot;
+    }
+}
+
+// One thread per pixel of the bucket: sum XYZ::from_spectral_sample(path)/spp over the pixel's samples.
+// out: image with row stride `stride` pixels whose origin is pixel (ox, oy).
+__global__ void __launch_bounds__(128) k_film(PathPool P, Bucket b, float* out, uint32_t stride, uint32_t ox,
+                                              uint32_t oy, float* samples_out) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= b.w * b.h) return;
+    uint32_t px = b.x + (q % b.w), py = b.y + (q / b.w);
+    V3 acc = mk3(0, 0, 0);
+    float fspp = (float)b.spp;
+    for (uint32_t si = 0; si < b.spp; ++si) {
+        uint32_t slot = q * b.spp + si;
+        float4 c = P.color[slot];
+        if (samples_out) reinterpret_cast<float4*>(samples_out)[slot] = c;
+        V3 xyz = xyz_from_spectral(from_f4(c), P.wavelength[slot]);
+        acc = acc + mk3(xyz.x / fspp, xyz.y / fspp, xyz.z / fspp);
+    }
+    if (out) {
+        float* o = out + ((size_t)(py - oy) * stride + (px - ox)) * 3;
+        o[0] = acc.x, o[1] = acc.y, o[2] = acc.z;
+    }
+}
+
+}  // namespace psyd

@@ -1,0 +1,898 @@
+// psy_cuda.cu — implementation of the C ABI in include/psy_cuda.h: scene upload, the wavefront
+// driver and the probe-ray entry.  Everything that computes runs in the CUDA kernels of
+// kernels.cuh; there is no CPU fallback (psy_init fails without a device).
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../host/hmath.h"
+#include "kernels.cuh"
+
+#define MENG_TABLE_QUAL static const
+#include "../../../tables/meng_tables.inc"
+#define SOBOL_TABLE_QUAL static const
+#include "../../../tables/sobol_tables.inc"
+
+using namespace psyd;
+
+namespace {
+
+thread_local std::string g_err;
+int32_t fail(int32_t code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(PSY_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));               \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t n) {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = n;
+        return cudaMalloc(&p, n ? n : 16);
+    }
+    template <typename T>
+    cudaError_t upload(const T* src, size_t count, cudaStream_t s) {
+        cudaError_t e = alloc(count * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (count) return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
+        return cudaSuccess;
+    }
+    template <typename T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+}  // namespace
+
+struct PsyContext {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+};
+
+struct PsyScene {
+    PsyContext* ctx = nullptr;
+    DScene d{};
+    uint32_t res_x = 0, res_y = 0, spp = 0, seed = 0;
+    uint64_t upload_bytes = 0;
+    DevBuf nodes, motion, tri_verts, tris, normals, meshes, lights, light_shape, light_colors, objects, shaders,
+        assemblies, instances, light_instances, light_inst_local, xforms, light_nodes, lt_bounds, paths, path_xforms,
+        path_inv, cam_xforms, cam_tfovs, cam_aperture, cam_focus, distant, world_floats, meng;
+    // path pool
+    size_t pool_cap = 0;
+    DevBuf pool_ray_o, pool_ray_d, pool_flags, pool_sseed, pool_wl, pool_cpdf, pool_nb_o, pool_nb_d, pool_next_atten,
+        pool_light_atten, pool_pending, pool_color, pool_hits, active_a, active_b;
+    DevBuf counts, fetch, counters, image, bucket_out, samples_out;
+    size_t counts_cap = 0;
+    std::vector<cudaEvent_t> events;
+    size_t events_used = 0;
+    double last_trace_ms = 0.0;
+    uint64_t last_trace_launches = 0;
+    std::mutex mu;
+    ~PsyScene() {
+        for (auto e : events) cudaEventDestroy(e);
+    }
+};
+
+namespace {
+
+using HXf = psyh::Xf;
+
+HXf xf_from_abi(const PsyXform& p) {
+    HXf m;
+    m.X = psyh::v3(p.r[0][0], p.r[1][0], p.r[2][0]);
+    m.Y = psyh::v3(p.r[0][1], p.r[1][1], p.r[2][1]);
+    m.Z = psyh::v3(p.r[0][2], p.r[1][2], p.r[2][2]);
+    m.T = psyh::v3(p.r[0][3], p.r[1][3], p.r[2][3]);
+    return m;
+}
+
+// TransformStack::push (transform_stack.rs:33-62): compose parent keys with child keys
+std::vector<HXf> compose(const std::vector<HXf>& parent, const std::vector<HXf>& child) {
+    if (parent.empty()) return child;
+    size_t n1 = parent.size(), n = child.size();
+    std::vector<HXf> out(std::max(n1, n));
+    if (n1 == n) {
+        for (size_t i = 0; i < n; ++i) out[i] = psyh::xf_mul(parent[i], child[i]);
+    } else if (n1 > n) {
+        float s = (float)(n1 - 1);
+        for (size_t i = 0; i < n1; ++i) out[i] = psyh::xf_mul(parent[i], psyh::lerp_slice(child.data(), n, (float)i / s));
+    } else {
+        float s = (float)(n - 1);
+        for (size_t i = 0; i < n; ++i) out[i] = psyh::xf_mul(psyh::lerp_slice(parent.data(), n1, (float)i / s), child[i]);
+    }
+    return out;
+}
+
+struct HostPath {
+    DPath d;
+    std::vector<HXf> keys;  // composed keys (empty = none)
+};
+
+int32_t validate(const PsySceneDesc* s) {
+    if (!s) return fail(PSY_ERR_INVALID, "null scene description");
+    if (s->abi_version != PSY_ABI_VERSION) return fail(PSY_ERR_INVALID, "PsySceneDesc.abi_version mismatch");
+    if (s->res_x == 0 || s->res_y == 0 || s->res_x > 65535 || s->res_y > 65535)
+        return fail(PSY_ERR_INVALID, "resolution must be in 1..65535");
+    if (s->n_assemblies == 0 || s->root_assembly >= s->n_assemblies) return fail(PSY_ERR_INVALID, "bad root assembly");
+    if (s->camera.n_xforms == 0 || s->camera.n_tfovs == 0 || s->camera.n_aperture_radii == 0 ||
+        s->camera.n_focus_distances == 0)
+        return fail(PSY_ERR_INVALID, "camera needs transforms, fovs, aperture and focus keys");
+    for (uint32_t i = 0; i < s->n_instances; ++i) {
+        const PsyInstance& in = s->instances[i];
+        if (in.kind == PSY_INSTANCE_OBJECT ? in.data_index >= s->n_objects : in.data_index >= s->n_assemblies)
+            return fail(PSY_ERR_INVALID, "instance data_index out of range");
+        if (in.shader_index != PSY_NONE && in.shader_index >= s->n_shaders)
+            return fail(PSY_ERR_INVALID, "instance shader_index out of range");
+        if ((uint64_t)in.xform_base + in.xform_count > s->n_xforms) return fail(PSY_ERR_INVALID, "instance xform range");
+    }
+    for (uint32_t i = 0; i < s->n_objects; ++i) {
+        const PsyObject& o = s->objects[i];
+        if (o.kind == PSY_OBJECT_MESH ? o.index >= s->n_meshes : o.index >= s->n_lights)
+            return fail(PSY_ERR_INVALID, "object index out of range");
+    }
+    for (uint32_t i = 0; i < s->n_nodes; ++i) {
+        const PsyBvh4Node& n = s->nodes[i];
+        if (n.n_children < 2 || n.n_children > 4 || n.traversal_code >= 48 || n.n_keys == 0)
+            return fail(PSY_ERR_INVALID, "malformed BVH4 node");
+        if (n.n_keys > 1 && (uint64_t)n.key_base + n.n_keys > s->n_motion_bounds)
+            return fail(PSY_ERR_INVALID, "BVH4 node key range");
+        for (uint32_t c = 0; c < n.n_children; ++c) {
+            uint32_t r = n.child[c];
+            if (r == PSY_NONE) return fail(PSY_ERR_INVALID, "BVH4 node with missing child");
+            if (!PSY_CHILD_IS_LEAF(r) && r >= s->n_nodes) return fail(PSY_ERR_INVALID, "BVH4 child out of range");
+        }
+    }
+    for (uint32_t i = 0; i < s->n_assemblies; ++i) {
+        const PsyAssembly& a = s->assemblies[i];
+        if ((uint64_t)a.instance_base + a.instance_count > s->n_instances ||
+            (uint64_t)a.light_instance_base + a.light_instance_count > s->n_light_instances)
+            return fail(PSY_ERR_INVALID, "assembly instance range");
+    }
+    return PSY_OK;
+}
+
+// Worst-case traversal stack depth (see dtrace.cuh): 3*depth+2 entries per BVH4 plus one marker.
+uint32_t stack_need(const PsySceneDesc* s, uint32_t asm_index, std::vector<int64_t>& memo, int nest, int& max_nest) {
+    if (memo[asm_index] >= 0) return (uint32_t)memo[asm_index];
+    max_nest = std::max(max_nest, nest);
+    const PsyAssembly& a = s->assemblies[asm_index];
+    uint32_t own = 3 * a.bvh_depth + 2 + 1;
+    uint32_t worst = 0;
+    if (nest < 64) {
+        for (uint32_t i = 0; i < a.instance_count; ++i) {
+            const PsyInstance& in = s->instances[a.instance_base + i];
+            uint32_t c = 0;
+            if (in.kind == PSY_INSTANCE_ASSEMBLY) {
+                c = stack_need(s, in.data_index, memo, nest + 1, max_nest);
+            } else if (s->objects[in.data_index].kind == PSY_OBJECT_MESH) {
+                c = 3 * s->meshes[s->objects[in.data_index].index].bvh_depth + 2 + 1;
+            }
+            worst = std::max(worst, c);
+        }
+    }
+    memo[asm_index] = own + worst;
+    return own + worst;
+}
+
+PathPool make_pool(PsyScene* sc) {
+    PathPool P;
+    P.ray_o = sc->pool_ray_o.as<float4>();
+    P.ray_d = sc->pool_ray_d.as<float4>();
+    P.flags = sc->pool_flags.as<uint32_t>();
+    P.sseed = sc->pool_sseed.as<uint32_t>();
+    P.wavelength = sc->pool_wl.as<float>();
+    P.closure_pdf = sc->pool_cpdf.as<float>();
+    P.nb_o = sc->pool_nb_o.as<float4>();
+    P.nb_d = sc->pool_nb_d.as<float4>();
+    P.next_atten = sc->pool_next_atten.as<float4>();
+    P.light_atten = sc->pool_light_atten.as<float4>();
+    P.pending = sc->pool_pending.as<float4>();
+    P.color = sc->pool_color.as<float4>();
+    P.hits = sc->pool_hits.as<HitRec>();
+    return P;
+}
+
+int32_t ensure_pool(PsyScene* sc, size_t n) {
+    if (n <= sc->pool_cap) return PSY_OK;
+    size_t cap = n;
+    CK(sc->pool_ray_o.alloc(cap * 16));
+    CK(sc->pool_ray_d.alloc(cap * 16));
+    CK(sc->pool_flags.alloc(cap * 4));
+    CK(sc->pool_sseed.alloc(cap * 4));
+    CK(sc->pool_wl.alloc(cap * 4));
+    CK(sc->pool_cpdf.alloc(cap * 4));
+    CK(sc->pool_nb_o.alloc(cap * 16));
+    CK(sc->pool_nb_d.alloc(cap * 16));
+    CK(sc->pool_next_atten.alloc(cap * 16));
+    CK(sc->pool_light_atten.alloc(cap * 16));
+    CK(sc->pool_pending.alloc(cap * 16));
+    CK(sc->pool_color.alloc(cap * 16));
+    CK(sc->pool_hits.alloc(cap * sizeof(HitRec)));
+    CK(sc->active_a.alloc(cap * 4));
+    CK(sc->active_b.alloc(cap * 4));
+    sc->pool_cap = cap;
+    return PSY_OK;
+}
+
+constexpr int WAVES = 6;           // camera, shadow, bounce1, shadow, bounce2, shadow (renderer.rs:599)
+constexpr int COUNT_SLOTS = 8;     // per bucket: counts[0..6]
+constexpr size_t DEFAULT_POOL = 4u << 20;
+
+int32_t ensure_counts(PsyScene* sc, size_t n_buckets) {
+    if (n_buckets <= sc->counts_cap) return PSY_OK;
+    CK(sc->counts.alloc(n_buckets * COUNT_SLOTS * 4));
+    CK(sc->fetch.alloc(n_buckets * COUNT_SLOTS * 4));
+    sc->counts_cap = n_buckets;
+    return PSY_OK;
+}
+
+cudaEvent_t next_event(PsyScene* sc) {
+    if (sc->events_used == sc->events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        sc->events.push_back(e);
+    }
+    return sc->events[sc->events_used++];
+}
+
+struct StageEvents {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gen, trace, shade, film;
+};
+
+// Enqueues the whole wavefront for one bucket on the scene's stream (no host synchronisation).
+int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float* out, uint32_t stride, uint32_t ox,
+                       uint32_t oy, float* samples_out, bool counters, StageEvents* ev, uint64_t* launches) {
+    cudaStream_t st = sc->ctx->stream;
+    uint32_t n = b.w * b.h * b.spp;
+    PathPool P = make_pool(sc);
+    uint32_t* counts = sc->counts.as<uint32_t>() + bucket_index * COUNT_SLOTS;
+    uint32_t* fetch = sc->fetch.as<uint32_t>() + bucket_index * COUNT_SLOTS;
+    uint32_t* act[2] = {sc->active_a.as<uint32_t>(), sc->active_b.as<uint32_t>()};
+    auto stamp = [&](std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* v, bool begin) {
+        if (!ev) return;
+        cudaEvent_t e = next_event(sc);
+        cudaEventRecord(e, st);
+        if (begin)
+            v->push_back({e, nullptr});
+        else
+            v->back().second = e;
+    };
+    int sms = sc->ctx->sm_count;
+    stamp(ev ? &ev->gen : nullptr, true);
+    k_generate<<<(n + 255) / 256, 256, 0, st>>>(sc->d, P, b, n, act[0], counts);
+    stamp(ev ? &ev->gen : nullptr, false);
+    *launches += 1;
+    uint32_t trace_blocks = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 12);
+    uint32_t shade_blocks = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 16);
+    for (int w = 0; w < WAVES; ++w) {
+        stamp(ev ? &ev->trace : nullptr, true);
+        if (counters)
+            k_trace<true><<<trace_blocks, 128, 0, st>>>(sc->d, P, act[w & 1], counts + w, fetch + w,
+                                                        sc->counters.as<TraceCounters>());
+        else
+            k_trace<false><<<trace_blocks, 128, 0, st>>>(sc->d, P, act[w & 1], counts + w, fetch + w, nullptr);
+        stamp(ev ? &ev->trace : nullptr, false);
+        stamp(ev ? &ev->shade : nullptr, true);
+        k_shade<<<shade_blocks, 128, 0, st>>>(sc->d, P, b, act[w & 1], counts + w, act[(w + 1) & 1], counts + w + 1);
+        stamp(ev ? &ev->shade : nullptr, false);
+        *launches += 2;
+    }
+    stamp(ev ? &ev->film : nullptr, true);
+    k_film<<<(b.w * b.h + 127) / 128, 128, 0, st>>>(P, b, out, stride, ox, oy, samples_out);
+    stamp(ev ? &ev->film : nullptr, false);
+    *launches += 1;
+    CK(cudaGetLastError());
+    return PSY_OK;
+}
+
+double sum_ms(const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v) {
+    double t = 0.0;
+    for (auto& p : v) {
+        float ms = 0.0f;
+        if (p.second && cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) t += ms;
+    }
+    return t;
+}
+
+// Renderer::render's bucket list (renderer.rs:138-180) for a pool of `spb` paths
+std::vector<Bucket> make_buckets(uint32_t width, uint32_t height, uint32_t start_x, uint32_t start_y, uint32_t spp,
+                                 uint32_t seed, size_t spb) {
+    double target = (double)spb / (double)spp;
+    uint32_t bdim = std::sqrt(target) < 1.0 ? 1u : (uint32_t)std::sqrt(target);
+    std::vector<Bucket> jobs;
+    uint32_t cx = width / bdim + 1, cy = height / bdim + 1;
+    uint32_t larger = std::max(cx, cy), pow2 = 1;
+    while (pow2 < larger) pow2 <<= 1;
+    uint64_t bucket_n = (uint64_t)pow2 * pow2;
+    for (uint64_t hd = 0; hd < bucket_n; ++hd) {
+        // hilbert::d2xy (hilbert.rs:47-63)
+        uint32_t x = 0, y = 0, t = (uint32_t)hd;
+        for (uint32_t s = 1; s < (1u << 16); s <<= 1) {
+            uint32_t rx = 1 & (t >> 1);
+            uint32_t ry = 1 & (t ^ rx);
+            if (ry == 0) {
+                if (rx == 1) {
+                    x = (s - 1) - x;
+                    y = (s - 1) - y;
+                }
+                std::swap(x, y);
+            }
+            x += s * rx;
+            y += s * ry;
+            t >>= 2;
+        }
+        uint64_t bx = (uint64_t)x * bdim, by = (uint64_t)y * bdim;
+        if (bx >= width || by >= height) continue;
+        uint32_t w = (uint32_t)std::min<uint64_t>(bdim, width - bx), h = (uint32_t)std::min<uint64_t>(bdim, height - by);
+        if (w > 0 && h > 0) jobs.push_back(Bucket{start_x + (uint32_t)bx, start_y + (uint32_t)by, w, h, spp, seed});
+    }
+    return jobs;
+}
+
+int32_t render_buckets(PsyScene* sc, const std::vector<Bucket>& jobs, bool counters, PsyStats* stats, float* host_out,
+                       psy_bucket_cb cb, void* user) {
+    cudaStream_t st = sc->ctx->stream;
+    auto t0 = std::chrono::steady_clock::now();
+    size_t max_n = 0;
+    for (auto& b : jobs) max_n = std::max(max_n, (size_t)b.w * b.h * b.spp);
+    int32_t rc = ensure_pool(sc, max_n);
+    if (rc) return rc;
+    rc = ensure_counts(sc, jobs.size());
+    if (rc) return rc;
+    if (!sc->image.p) {
+        CK(sc->image.alloc((size_t)sc->res_x * sc->res_y * 3 * sizeof(float)));
+        CK(cudaMemsetAsync(sc->image.p, 0, sc->image.bytes, st));
+    }
+    if (!sc->counters.p) CK(sc->counters.alloc(sizeof(TraceCounters)));
+    CK(cudaMemsetAsync(sc->counters.p, 0, sizeof(TraceCounters), st));
+    if (!jobs.empty()) {
+        CK(cudaMemsetAsync(sc->counts.p, 0, jobs.size() * COUNT_SLOTS * 4, st));
+        CK(cudaMemsetAsync(sc->fetch.p, 0, jobs.size() * COUNT_SLOTS * 4, st));
+    }
+    sc->events_used = 0;
+    StageEvents ev;
+    uint64_t launches = 0;
+    std::vector<float> cb_buf;
+    for (size_t j = 0; j < jobs.size(); ++j) {
+        const Bucket& b = jobs[j];
+        rc = enqueue_bucket(sc, b, j, sc->image.as<float>(), sc->res_x, 0, 0, nullptr, counters, &ev, &launches);
+        if (rc) return rc;
+        if (cb) {
+            // Blender-style streaming: hand the finished bucket to the caller (renderer.rs:312-346)
+            cb_buf.resize((size_t)b.w * b.h * 3);
+            CK(cudaMemcpy2DAsync(cb_buf.data(), (size_t)b.w * 12, sc->image.as<float>() + ((size_t)b.y * sc->res_x + b.x) * 3,
+                                 (size_t)sc->res_x * 12, (size_t)b.w * 12, b.h, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            cb(user, b.x, b.y, b.x + b.w, b.y + b.h, cb_buf.data());
+        }
+    }
+    if (host_out)
+        CK(cudaMemcpyAsync(host_out, sc->image.p, sc->image.bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+
+    std::vector<uint32_t> counts(jobs.size() * COUNT_SLOTS);
+    if (!jobs.empty()) CK(cudaMemcpy(counts.data(), sc->counts.p, counts.size() * 4, cudaMemcpyDeviceToHost));
+    uint64_t rays = 0, samples = 0;
+    for (size_t j = 0; j < jobs.size(); ++j) {
+        for (int w = 0; w < WAVES; ++w) rays += counts[j * COUNT_SLOTS + w];
+        samples += (uint64_t)jobs[j].w * jobs[j].h * jobs[j].spp;
+    }
+    TraceCounters tc{};
+    if (counters) CK(cudaMemcpy(&tc, sc->counters.p, sizeof(tc), cudaMemcpyDeviceToHost));
+    sc->last_trace_ms = sum_ms(ev.trace);
+    sc->last_trace_launches = ev.trace.size();
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->trace_time = sc->last_trace_ms * 1e-3;
+        stats->initial_ray_generation_time = sum_ms(ev.gen) * 1e-3;
+        stats->ray_generation_time = sum_ms(ev.shade) * 1e-3;
+        stats->sample_writing_time = sum_ms(ev.film) * 1e-3;
+        stats->total_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        stats->ray_count = rays;
+        stats->accel_node_visits = tc.node_visits;
+        stats->tri_tests = tc.tri_tests;
+        stats->instance_visits = tc.instance_visits;
+        stats->motion_node_visits = tc.motion_node_visits;
+        stats->samples = samples;
+        stats->kernel_launches = launches;
+    }
+    return PSY_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* psy_last_error(void) { return g_err.c_str(); }
+int32_t psy_abi_version(void) { return PSY_ABI_VERSION; }
+
+int32_t psy_init(const int* device_ids, int n_devices, PsyContext** out) {
+    if (!out) return fail(PSY_ERR_INVALID, "psy_init: out is null");
+    if (n_devices > 1)
+        return fail(PSY_ERR_INVALID, "one context drives one GPU: launch one process per GPU (torchrun) and shard tiles");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(PSY_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                           " (this library has no CPU fallback)");
+    int dev = (device_ids && n_devices == 1) ? device_ids[0] : 0;
+    if (dev < 0 || dev >= count) return fail(PSY_ERR_INVALID, "device id out of range");
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    PsyContext* c = new PsyContext();
+    c->device = dev;
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // static tables
+    uint8_t table[8][48];
+    for (int raydir = 0; raydir < 8; ++raydir) {
+        // TRAVERSAL_TABLE (sub_crates/bvh_order/build.rs:17-75)
+        int ray[3] = {raydir & 1, (raydir >> 1) & 1, (raydir >> 2) & 1};
+        int n = 0;
+        for (int s2 = 0; s2 < 3; ++s2)
+            for (int s1 = 0; s1 < 3; ++s1)
+                for (int s0 = 0; s0 < 3; ++s0) {
+                    int perm[4] = {0, 1, 2, 3};
+                    if (ray[s1]) std::swap(perm[0], perm[1]);
+                    if (ray[s2]) std::swap(perm[2], perm[3]);
+                    if (ray[s0]) {
+                        std::swap(perm[0], perm[2]);
+                        std::swap(perm[1], perm[3]);
+                    }
+                    table[raydir][n++] = (uint8_t)(perm[0] + (perm[1] << 2) + (perm[2] << 4) + (perm[3] << 6));
+                }
+        for (int s1 = 0; s1 < 3; ++s1)
+            for (int s0 = 0; s0 < 3; ++s0) {
+                int perm[3] = {0, 1, 2};
+                if (ray[s1]) std::swap(perm[0], perm[1]);
+                if (ray[s0]) {
+                    std::swap(perm[0], perm[1]);
+                    std::swap(perm[0], perm[2]);
+                }
+                table[raydir][n++] = (uint8_t)(perm[0] + (perm[1] << 2) + (perm[2] << 4));
+            }
+        for (int s1 = 0; s1 < 3; ++s1)
+            for (int s0 = 0; s0 < 3; ++s0) {
+                int perm[3] = {0, 1, 2};
+                if (ray[s1]) std::swap(perm[1], perm[2]);
+                if (ray[s0]) {
+                    std::swap(perm[0], perm[2]);
+                    std::swap(perm[0], perm[1]);
+                }
+                table[raydir][n++] = (uint8_t)(perm[0] + (perm[1] << 2) + (perm[2] << 4));
+            }
+        for (int s0 = 0; s0 < 3; ++s0) {
+            int perm[2] = {0, 1};
+            if (ray[s0]) std::swap(perm[0], perm[1]);
+            table[raydir][n++] = (uint8_t)(perm[0] + (perm[1] << 2));
+        }
+    }
+    CK(cudaMemcpyToSymbol(c_traversal_table, table, sizeof(table)));
+    CK(cudaMemcpyToSymbol(c_sobol_rev, SOBOL_REV_VECTORS, sizeof(SOBOL_REV_VECTORS)));
+    CK(cudaMemcpyToSymbol(c_meng_grid, MENG_GRID, sizeof(MENG_GRID)));
+    CK(cudaMemcpyToSymbol(c_meng_uv, MENG_UV, sizeof(MENG_UV)));
+    CK(cudaMemcpyToSymbol(c_meng_mat, MENG_MAT_XY_TO_UV, sizeof(MENG_MAT_XY_TO_UV)));
+    *out = c;
+    return PSY_OK;
+}
+
+int32_t psy_shutdown(PsyContext* ctx) {
+    if (!ctx) return PSY_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PSY_OK;
+}
+
+int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out) {
+    if (!ctx || !out) return fail(PSY_ERR_INVALID, "psy_scene_create: null argument");
+    int32_t rc = validate(s);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+
+    // stack requirement
+    {
+        std::vector<int64_t> memo(s->n_assemblies, -1);
+        int max_nest = 0;
+        uint32_t need = stack_need(s, s->root_assembly, memo, 0, max_nest);
+        if (need > (uint32_t)TRACE_STACK_SIZE)
+            return fail(PSY_ERR_LIMIT, "scene needs a traversal stack of " + std::to_string(need) + " entries, limit is " +
+                                           std::to_string(TRACE_STACK_SIZE));
+        if (max_nest >= TRACE_MAX_NEST) return fail(PSY_ERR_LIMIT, "assembly nesting deeper than TRACE_MAX_NEST");
+    }
+
+    // expand instance paths breadth-first and compose their transforms
+    std::vector<HostPath> paths;
+    {
+        struct Item {
+            uint32_t path, assembly;
+        };
+        std::vector<Item> queue;
+        auto add_children = [&](uint32_t asm_index, const std::vector<HXf>& parent_keys) -> int32_t {
+            const PsyAssembly& a = s->assemblies[asm_index];
+            if (paths.size() + a.instance_count > (1u << 26)) return fail(PSY_ERR_LIMIT, "more than 2^26 instance paths");
+            uint32_t base = (uint32_t)paths.size();
+            for (uint32_t i = 0; i < a.instance_count; ++i) {
+                const PsyInstance& in = s->instances[a.instance_base + i];
+                HostPath hp;
+                hp.d.inst = a.instance_base + i;
+                hp.d.child_base = PSY_NONE;
+                if (in.xform_count > 0) {
+                    std::vector<HXf> own(in.xform_count);
+                    for (uint32_t k = 0; k < in.xform_count; ++k) own[k] = xf_from_abi(s->xforms[in.xform_base + k]);
+                    hp.keys = compose(parent_keys, own);
+                } else {
+                    hp.keys = parent_keys;
+                }
+                paths.push_back(std::move(hp));
+                if (in.kind == PSY_INSTANCE_ASSEMBLY) queue.push_back({base + i, in.data_index});
+            }
+            return PSY_OK;
+        };
+        rc = add_children(s->root_assembly, {});
+        if (rc) return rc;
+        for (size_t q = 0; q < queue.size(); ++q) {
+            Item it = queue[q];
+            paths[it.path].d.child_base = (uint32_t)paths.size();
+            std::vector<HXf> keys = paths[it.path].keys;
+            rc = add_children(it.assembly, keys);
+            if (rc) return rc;
+        }
+    }
+    std::vector<DPath> dpaths(paths.size());
+    std::vector<PsyXform> path_xf, path_inv(paths.size());
+    for (size_t i = 0; i < paths.size(); ++i) {
+        paths[i].d.xf_base = (uint32_t)path_xf.size();
+        paths[i].d.xf_count = (uint32_t)paths[i].keys.size();
+        for (auto& k : paths[i].keys) path_xf.push_back(psyh::to_abi(k));
+        path_inv[i] = psyh::to_abi(paths[i].keys.size() == 1 ? psyh::xf_inverse(paths[i].keys[0]) : HXf());
+        dpaths[i] = paths[i].d;
+    }
+
+    // gather triangle vertices per leaf-ordered triangle: [v0 keys][v1 keys][v2 keys]
+    std::vector<DMesh> dmeshes(s->n_meshes);
+    size_t tv_total = 0;
+    for (uint32_t m = 0; m < s->n_meshes; ++m) tv_total += (size_t)s->meshes[m].tri_count * 3 * s->meshes[m].n_keys;
+    if (tv_total > 0xFFFFFFFFull) return fail(PSY_ERR_LIMIT, "gathered triangle vertex array exceeds 2^32 entries");
+    std::vector<float4> tri_verts(tv_total);
+    {
+        size_t o = 0;
+        for (uint32_t m = 0; m < s->n_meshes; ++m) {
+            const PsyMesh& pm = s->meshes[m];
+            DMesh& dm = dmeshes[m];
+            dm.root = pm.root, dm.tri_base = pm.tri_base, dm.tri_count = pm.tri_count, dm.n_keys = pm.n_keys;
+            dm.tv_base = (uint32_t)o;
+            dm.vert_base = pm.vert_base;
+            dm.has_normals = pm.has_normals;
+            dm.pad = 0;
+            uint32_t k = pm.n_keys;
+            if ((uint64_t)pm.tri_base + pm.tri_count > s->n_tris) return fail(PSY_ERR_INVALID, "mesh triangle range");
+            for (uint32_t t = 0; t < pm.tri_count; ++t) {
+                const uint32_t* idx = s->tris + (size_t)(pm.tri_base + t) * 4;
+                for (int j = 0; j < 3; ++j) {
+                    if (idx[j] >= pm.vert_count) return fail(PSY_ERR_INVALID, "triangle vertex index out of range");
+                    for (uint32_t key = 0; key < k; ++key) {
+                        const float* v = s->verts + ((size_t)pm.vert_base + (size_t)idx[j] * k + key) * 3;
+                        float w = 0.0f;
+                        if (j == 0 && key == 0) std::memcpy(&w, &idx[3], 4);
+                        tri_verts[o++] = make_float4(v[0], v[1], v[2], w);
+                    }
+                }
+            }
+        }
+    }
+    std::vector<float4> normals4(s->n_vert_keys);
+    bool any_normals = false;
+    for (uint32_t m = 0; m < s->n_meshes; ++m) any_normals |= s->meshes[m].has_normals != 0;
+    if (any_normals)
+        for (uint32_t i = 0; i < s->n_vert_keys; ++i)
+            normals4[i] = make_float4(s->normals[3 * (size_t)i], s->normals[3 * (size_t)i + 1], s->normals[3 * (size_t)i + 2], 0.0f);
+    else
+        normals4.clear();
+
+    // light instance -> index of the same instance inside its assembly's instance list
+    std::vector<uint32_t> light_local(s->n_light_instances, PSY_NONE);
+    for (uint32_t a = 0; a < s->n_assemblies; ++a) {
+        const PsyAssembly& pa = s->assemblies[a];
+        for (uint32_t li = 0; li < pa.light_instance_count; ++li)
+            for (uint32_t i = 0; i < pa.instance_count; ++i)
+                if (s->instances[pa.instance_base + i].id == s->light_instances[pa.light_instance_base + li].id) {
+                    light_local[pa.light_instance_base + li] = i;
+                    break;
+                }
+    }
+
+    PsyScene* sc = new PsyScene();
+    sc->ctx = ctx;
+    sc->res_x = s->res_x, sc->res_y = s->res_y, sc->spp = s->spp, sc->seed = s->seed;
+#define UP(buf, ptr, n)                                                       \
+    do {                                                                      \
+        cudaError_t e_ = sc->buf.upload(ptr, n, st);                          \
+        if (e_ != cudaSuccess) {                                              \
+            delete sc;                                                        \
+            return fail(PSY_ERR_CUDA, std::string("upload " #buf ": ") + cudaGetErrorString(e_)); \
+        }                                                                     \
+        sc->upload_bytes += sc->buf.bytes;                                    \
+    } while (0)
+    UP(nodes, s->nodes, (size_t)s->n_nodes);
+    UP(motion, s->motion_bounds, (size_t)s->n_motion_bounds);
+    UP(tri_verts, tri_verts.data(), tri_verts.size());
+    UP(tris, s->tris, (size_t)s->n_tris * 4);
+    UP(normals, normals4.data(), normals4.size());
+    UP(meshes, dmeshes.data(), dmeshes.size());
+    UP(lights, s->lights, (size_t)s->n_lights);
+    UP(light_shape, s->light_shape, (size_t)s->n_light_shape);
+    UP(light_colors, s->light_colors, (size_t)s->n_light_colors);
+    UP(objects, s->objects, (size_t)s->n_objects);
+    UP(shaders, s->shaders, (size_t)s->n_shaders);
+    UP(assemblies, s->assemblies, (size_t)s->n_assemblies);
+    UP(instances, s->instances, (size_t)s->n_instances);
+    UP(light_instances, s->light_instances, (size_t)s->n_light_instances);
+    UP(light_inst_local, light_local.data(), light_local.size());
+    UP(xforms, s->xforms, (size_t)s->n_xforms);
+    UP(light_nodes, s->light_nodes, (size_t)s->n_light_nodes);
+    UP(lt_bounds, s->lt_bounds, (size_t)s->n_lt_bounds);
+    UP(paths, dpaths.data(), dpaths.size());
+    UP(path_xforms, path_xf.data(), path_xf.size());
+    UP(path_inv, path_inv.data(), path_inv.size());
+    UP(cam_xforms, s->camera.xforms, (size_t)s->camera.n_xforms);
+    UP(cam_tfovs, s->camera.tfovs, (size_t)s->camera.n_tfovs);
+    UP(cam_aperture, s->camera.aperture_radii, (size_t)s->camera.n_aperture_radii);
+    UP(cam_focus, s->camera.focus_distances, (size_t)s->camera.n_focus_distances);
+    UP(distant, s->distant_lights, (size_t)s->n_distant_lights);
+    UP(world_floats, s->world_floats, (size_t)s->n_world_floats);
+    UP(meng, &MENG_SPECTRA[0][0], (size_t)186 * 95);
+#undef UP
+    cudaError_t e = cudaStreamSynchronize(st);  // the staging vectors above die at return
+    if (e != cudaSuccess) {
+        delete sc;
+        return fail(PSY_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
+    }
+
+    DScene& d = sc->d;
+    d.nodes = sc->nodes.as<uint4>();
+    d.motion_bounds = sc->motion.as<float4>();
+    d.tri_verts = sc->tri_verts.as<float4>();
+    d.tris = sc->tris.as<uint4>();
+    d.normals = sc->normals.as<float4>();
+    d.meshes = sc->meshes.as<DMesh>();
+    d.lights = sc->lights.as<PsyLight>();
+    d.light_shape = sc->light_shape.as<float>();
+    d.light_colors = sc->light_colors.as<PsyColor>();
+    d.objects = sc->objects.as<PsyObject>();
+    d.shaders = sc->shaders.as<PsyShader>();
+    d.assemblies = sc->assemblies.as<PsyAssembly>();
+    d.instances = sc->instances.as<PsyInstance>();
+    d.light_instances = sc->light_instances.as<PsyInstance>();
+    d.light_inst_local = sc->light_inst_local.as<uint32_t>();
+    d.xforms = sc->xforms.as<float4>();
+    d.light_nodes = sc->light_nodes.as<PsyLightNode>();
+    d.lt_bounds = sc->lt_bounds.as<PsyBBox>();
+    d.paths = sc->paths.as<DPath>();
+    d.path_xforms = sc->path_xforms.as<float4>();
+    d.path_inv = sc->path_inv.as<float4>();
+    d.root_assembly = s->root_assembly;
+    d.n_paths = (uint32_t)dpaths.size();
+    d.cam_xforms = sc->cam_xforms.as<float4>();
+    d.cam_tfovs = sc->cam_tfovs.as<float>();
+    d.cam_aperture = sc->cam_aperture.as<float>();
+    d.cam_focus = sc->cam_focus.as<float>();
+    d.n_cam_xforms = s->camera.n_xforms;
+    d.n_cam_tfovs = s->camera.n_tfovs;
+    d.n_cam_aperture = s->camera.n_aperture_radii;
+    d.n_cam_focus = s->camera.n_focus_distances;
+    d.background = s->background;
+    d.distant_lights = sc->distant.as<PsyDistantLight>();
+    d.world_floats = sc->world_floats.as<float>();
+    d.n_distant_lights = s->n_distant_lights;
+    {
+        // fold of approximate_energy over the world lights (scene/mod.rs:44-53)
+        float sum = 0.0f;
+        for (uint32_t i = 0; i < s->n_distant_lights; ++i) {
+            const PsyDistantLight& l = s->distant_lights[i];
+            float a = 0.0f;
+            for (uint32_t k = 0; k < l.n_colors; ++k) {
+                const PsyColor& c = s->light_colors[l.color_base + k];
+                float en = c.kind == PSY_COLOR_BLACKBODY ? (c.a * c.a) * (c.a * c.a) * c.b : c.b;
+                a = a + en;
+            }
+            sum = sum + a / (float)l.n_colors;
+        }
+        d.world_light_energy_sum = sum;
+    }
+    d.meng_spectra = sc->meng.as<float>();
+    d.res_x = s->res_x;
+    d.res_y = s->res_y;
+    *out = sc;
+    return PSY_OK;
+}
+
+int32_t psy_scene_destroy(PsyScene* scene) {
+    if (!scene) return PSY_OK;
+    cudaSetDevice(scene->ctx->device);
+    cudaStreamSynchronize(scene->ctx->stream);
+    delete scene;
+    return PSY_OK;
+}
+
+int32_t psy_trace_rays(PsyScene* sc, const PsyRay* rays, size_t n, PsyHit* hits, PsyHitGeo* geo) {
+    if (!sc || (!rays && n) || (!hits && n)) return fail(PSY_ERR_INVALID, "psy_trace_rays: null argument");
+    if (n == 0) return PSY_OK;
+    if (n > 0x7FFFFFFFull) return fail(PSY_ERR_INVALID, "too many rays in one call");
+    std::lock_guard<std::mutex> g(sc->mu);
+    CK(cudaSetDevice(sc->ctx->device));
+    cudaStream_t st = sc->ctx->stream;
+    DevBuf drays, dhits, dgeo;
+    CK(drays.upload(rays, n, st));
+    CK(dhits.alloc(n * sizeof(PsyHit)));
+    if (geo) CK(dgeo.alloc(n * sizeof(PsyHitGeo)));
+    k_trace_probe<false><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc->d, drays.as<PsyRay>(), (uint32_t)n,
+                                                                     dhits.as<PsyHit>(), geo ? dgeo.as<PsyHitGeo>() : nullptr,
+                                                                     nullptr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hits, dhits.p, n * sizeof(PsyHit), cudaMemcpyDeviceToHost, st));
+    if (geo) CK(cudaMemcpyAsync(geo, dgeo.p, n * sizeof(PsyHitGeo), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSY_OK;
+}
+
+static int32_t render_bucket_impl(PsyScene* sc, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint32_t spp, uint32_t seed,
+                                  float* xyz_out, float* samples_out, PsyStats* stats) {
+    if (!sc) return fail(PSY_ERR_INVALID, "null scene");
+    if (w == 0 || h == 0 || spp == 0) return fail(PSY_ERR_INVALID, "empty bucket");
+    if ((uint64_t)x + w > sc->res_x || (uint64_t)y + h > sc->res_y) return fail(PSY_ERR_INVALID, "bucket outside the image");
+    uint64_t n = (uint64_t)w * h * spp;
+    if (n > (1ull << 28)) return fail(PSY_ERR_LIMIT, "bucket has more than 2^28 paths");
+    std::lock_guard<std::mutex> g(sc->mu);
+    CK(cudaSetDevice(sc->ctx->device));
+    cudaStream_t st = sc->ctx->stream;
+    auto t0 = std::chrono::steady_clock::now();
+    int32_t rc = ensure_pool(sc, n);
+    if (rc) return rc;
+    rc = ensure_counts(sc, 1);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(sc->counts.p, 0, COUNT_SLOTS * 4, st));
+    CK(cudaMemsetAsync(sc->fetch.p, 0, COUNT_SLOTS * 4, st));
+    CK(sc->bucket_out.alloc((size_t)w * h * 3 * 4));
+    if (samples_out) CK(sc->samples_out.alloc(n * 16));
+    Bucket b{x, y, w, h, spp, seed};
+    sc->events_used = 0;
+    StageEvents ev;
+    uint64_t launches = 0;
+    rc = enqueue_bucket(sc, b, 0, sc->bucket_out.as<float>(), w, x, y, samples_out ? sc->samples_out.as<float>() : nullptr,
+                        false, &ev, &launches);
+    if (rc) return rc;
+    if (xyz_out) CK(cudaMemcpyAsync(xyz_out, sc->bucket_out.p, (size_t)w * h * 12, cudaMemcpyDeviceToHost, st));
+    if (samples_out) CK(cudaMemcpyAsync(samples_out, sc->samples_out.p, n * 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint32_t counts[COUNT_SLOTS];
+    CK(cudaMemcpy(counts, sc->counts.p, sizeof(counts), cudaMemcpyDeviceToHost));
+    sc->last_trace_ms = sum_ms(ev.trace);
+    sc->last_trace_launches = ev.trace.size();
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        for (int wv = 0; wv < WAVES; ++wv) stats->ray_count += counts[wv];
+        stats->trace_time = sc->last_trace_ms * 1e-3;
+        stats->initial_ray_generation_time = sum_ms(ev.gen) * 1e-3;
+        stats->ray_generation_time = sum_ms(ev.shade) * 1e-3;
+        stats->sample_writing_time = sum_ms(ev.film) * 1e-3;
+        stats->total_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        stats->samples = n;
+        stats->kernel_launches = launches;
+    }
+    return PSY_OK;
+}
+
+int32_t psy_render_bucket(PsyScene* sc, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint32_t spp, uint32_t seed,
+                          float* xyz_out, PsyStats* stats) {
+    return render_bucket_impl(sc, x, y, w, h, spp, seed, xyz_out, nullptr, stats);
+}
+
+int32_t psy_render_bucket_samples(PsyScene* sc, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint32_t spp,
+                                  uint32_t seed, float* samples_out, PsyStats* stats) {
+    if (!samples_out) return fail(PSY_ERR_INVALID, "samples_out is null");
+    return render_bucket_impl(sc, x, y, w, h, spp, seed, nullptr, samples_out, stats);
+}
+
+static int32_t image_jobs(PsyScene* sc, const PsyRenderParams* p, std::vector<Bucket>& jobs) {
+    uint32_t spp = (p && p->spp) ? p->spp : sc->spp;
+    uint32_t seed = (p && p->seed_override_enabled) ? p->seed : sc->seed;
+    if (spp == 0) return fail(PSY_ERR_INVALID, "spp is zero");
+    uint32_t width = sc->res_x, height = sc->res_y, sx = 0, sy = 0;
+    if (p && p->crop_enabled) {
+        // renderer.rs:100-108
+        uint32_t x1 = std::min(p->crop_x1, sc->res_x - 1), y1 = std::min(p->crop_y1, sc->res_y - 1);
+        uint32_t x2 = std::min(p->crop_x2, sc->res_x - 1), y2 = std::min(p->crop_y2, sc->res_y - 1);
+        if (x2 < x1 || y2 < y1) return fail(PSY_ERR_INVALID, "crop rectangle is inverted");
+        width = x2 - x1 + 1, height = y2 - y1 + 1, sx = x1, sy = y1;
+    }
+    size_t spb = (p && p->max_samples_per_bucket) ? p->max_samples_per_bucket : DEFAULT_POOL;
+    jobs = make_buckets(width, height, sx, sy, spp, seed, spb);
+    return PSY_OK;
+}
+
+int32_t psy_render_image(PsyScene* sc, const PsyRenderParams* p, float* xyz_out, PsyStats* stats, psy_bucket_cb cb,
+                         void* user) {
+    if (!sc) return fail(PSY_ERR_INVALID, "null scene");
+    bool resident = p && p->device_resident_only;
+    if (!xyz_out && !resident) return fail(PSY_ERR_INVALID, "xyz_out is null and device_resident_only is not set");
+    std::lock_guard<std::mutex> g(sc->mu);
+    CK(cudaSetDevice(sc->ctx->device));
+    std::vector<Bucket> jobs;
+    int32_t rc = image_jobs(sc, p, jobs);
+    if (rc) return rc;
+    if (sc->image.p) CK(cudaMemsetAsync(sc->image.p, 0, sc->image.bytes, sc->ctx->stream));
+    return render_buckets(sc, jobs, p && p->collect_counters, stats, resident ? nullptr : xyz_out, cb, user);
+}
+
+int32_t psy_render_image_shard(PsyScene* sc, const PsyRenderParams* p, uint32_t rank, uint32_t world, PsyStats* stats) {
+    if (!sc || world == 0 || rank >= world) return fail(PSY_ERR_INVALID, "bad shard arguments");
+    std::lock_guard<std::mutex> g(sc->mu);
+    CK(cudaSetDevice(sc->ctx->device));
+    std::vector<Bucket> all, mine;
+    int32_t rc = image_jobs(sc, p, all);
+    if (rc) return rc;
+    for (size_t j = 0; j < all.size(); ++j)
+        if (j % world == rank) mine.push_back(all[j]);
+    if (sc->image.p) CK(cudaMemsetAsync(sc->image.p, 0, sc->image.bytes, sc->ctx->stream));
+    return render_buckets(sc, mine, p && p->collect_counters, stats, nullptr, nullptr, nullptr);
+}
+
+int32_t psy_device_image(PsyScene* sc, void** dev_ptr, size_t* n_floats) {
+    if (!sc || !dev_ptr || !n_floats) return fail(PSY_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(sc->mu);
+    CK(cudaSetDevice(sc->ctx->device));
+    if (!sc->image.p) {
+        CK(sc->image.alloc((size_t)sc->res_x * sc->res_y * 3 * sizeof(float)));
+        CK(cudaMemsetAsync(sc->image.p, 0, sc->image.bytes, sc->ctx->stream));
+        CK(cudaStreamSynchronize(sc->ctx->stream));
+    }
+    *dev_ptr = sc->image.p;
+    *n_floats = (size_t)sc->res_x * sc->res_y * 3;
+    return PSY_OK;
+}
+
+int32_t psy_scene_stream(PsyScene* sc, void** cuda_stream) {
+    if (!sc || !cuda_stream) return fail(PSY_ERR_INVALID, "null argument");
+    *cuda_stream = (void*)sc->ctx->stream;
+    return PSY_OK;
+}
+
+int32_t psy_fetch_image(PsyScene* sc, float* xyz_out) {
+    if (!sc || !xyz_out) return fail(PSY_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(sc->mu);
+    CK(cudaSetDevice(sc->ctx->device));
+    if (!sc->image.p) return fail(PSY_ERR_INVALID, "no image has been rendered yet");
+    CK(cudaMemcpyAsync(xyz_out, sc->image.p, sc->image.bytes, cudaMemcpyDeviceToHost, sc->ctx->stream));
+    CK(cudaStreamSynchronize(sc->ctx->stream));
+    return PSY_OK;
+}
+
+int32_t psy_last_trace_timing(PsyScene* sc, double* total_ms, uint64_t* launches) {
+    if (!sc) return fail(PSY_ERR_INVALID, "null scene");
+    if (total_ms) *total_ms = sc->last_trace_ms;
+    if (launches) *launches = sc->last_trace_launches;
+    return PSY_OK;
+}
+
+}  // extern "C"
