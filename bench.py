@@ -1,0 +1,349 @@
+#!/usr/bin/env python3
+"""bench.py — Mrays/s (extend + shadow) of the render core on BASELINE.json's headline configuration.
+
+Workload (config C5): the synthetic hierarchical-instancing scene (100 cluster sub-assemblies x
+(10 instances of 4 unique 500k-triangle assets + 10 area lights) ~ 5e8 effective triangles, 1000 lights
+through nested light trees, moving cluster instances with 2 transform keys) at 3840x2160, 256 spp.
+
+A step = one full render of that image.  With N > 1 ranks (torchrun, one process per GPU) the
+Hilbert-ordered tiles are dealt round-robin to the ranks (scene replicated per GPU, no exchange while
+rendering) and the disjoint device tiles are summed onto rank 0 with one NCCL reduce per step;
+total work is fixed, so scaling is "strong".
+
+  value     whole-job Mrays/s, scene resident in HBM, image left on the device
+  e2e       the same metric through the C ABI with host buffers: every step uploads the scene
+            description (H2D) and fetches the finished image (D2H)
+  roofline  k_trace (the dominant kernel): algorithmic bytes of SURVEY.md 8(d)'s formula, with visit
+            counts measured by the counters build, over the CUDA-event time of the trace launches
+  cpu_baseline / --impl reference: the CPU oracle (restated reference path; the Rust reference cannot be
+            built here) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+WORKLOADS = {
+    # name: (scene kwargs, resolution, spp, seed)
+    "C5": dict(asset_quads=500, n_assets=4, n_clusters=100, inst_per_cluster=10, lights_per_cluster=10,
+               cluster_xform_keys=2, res=(3840, 2160), spp=256, seed=5),
+    "C4": dict(asset_quads=500, n_assets=4, n_clusters=100, inst_per_cluster=10, lights_per_cluster=10,
+               cluster_xform_keys=1, res=(1920, 1080), spp=64, seed=4),
+    "tiny": dict(asset_quads=40, n_assets=4, n_clusters=16, inst_per_cluster=6, lights_per_cluster=4,
+                 cluster_xform_keys=2, res=(320, 180), spp=8, seed=5),
+}
+WORKLOAD_DESC = {
+    "C5": "C5: synthetic hierarchical-instancing scene (100 clusters x (10 instances of 4 x 500k-tri assets + 10 area "
+          "lights), 2 transform keys per cluster instance), 3840x2160, 256 spp",
+    "C4": "C4: synthetic hierarchical-instancing scene, 1920x1080, 64 spp",
+    "tiny": "tiny instanced scene (harness self-test), 320x180, 8 spp",
+}
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_scene(name):
+    from psychopath_b200 import api
+    kw = dict(WORKLOADS[name])
+    t0 = time.time()
+    scene = api.Scene.synth_instanced(**kw)
+    return scene, time.time() - t0
+
+
+def algorithmic_bytes_per_ray(st, keys_node=1.0, keys_vert=1, keys_xform=1):
+    """B_ray = N_node*(16+96*k_n) + N_tri*(16+48*k_v) + N_inst*(32+48*k_x) + 48 + 32."""
+    rays = max(int(st["ray_count"]), 1)
+    n_node = st["accel_node_visits"] / rays
+    n_motion = st["motion_node_visits"] / rays
+    n_tri = st["tri_tests"] / rays
+    n_inst = st["instance_visits"] / rays
+    b = (n_node - n_motion) * (16 + 96) + n_motion * (16 + 96 * 2) + n_tri * (16 + 48 * keys_vert) + \
+        n_inst * (32 + 48 * keys_xform) + 48 + 32
+    return b, {"nodes_per_ray": n_node, "motion_nodes_per_ray": n_motion, "tris_per_ray": n_tri,
+               "instances_per_ray": n_inst}
+
+
+def cpu_sample(scene, spp, seed, target_s=15.0, threads=0):
+    """Times the oracle on a bounded number of Hilbert-ordered buckets of the same workload."""
+    import oracle_lib as O
+    nb = 64
+    _, st, done = O.render_image(scene.desc, spp, seed, spb=4096, threads=threads, max_buckets=nb)
+    rate = st.ray_count / max(st.total_time, 1e-9)
+    if st.total_time < target_s * 0.5:
+        nb = int(min(max(nb * target_s / max(st.total_time, 1e-3), nb), 1 << 22))
+        _, st, done = O.render_image(scene.desc, spp, seed, spb=4096, threads=threads, max_buckets=nb)
+        rate = st.ray_count / max(st.total_time, 1e-9)
+    return {"mrays_s": rate / 1e6, "msamples_s": st.samples / max(st.total_time, 1e-9) / 1e6, "seconds": st.total_time,
+            "buckets": done, "rays": int(st.ray_count), "samples": int(st.samples), "threads": int(st.threads)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    name = args.workload
+    kw = WORKLOADS[name]
+    scene, build_s = build_scene(name)
+    vals, last = [], None
+    per_step = max(3.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
+    for i in range(args.warmup + args.steps):
+        last = cpu_sample(scene, kw["spp"], kw["seed"], target_s=per_step)
+        if i >= args.warmup:
+            vals.append(last)
+    v = sum(x["mrays_s"] for x in vals) / len(vals)
+    ms = sum(x["seconds"] for x in vals) / len(vals) * 1e3
+    sample = (f"{last['buckets']} Hilbert-ordered 4x4-pixel buckets x {kw['spp']} spp of the same scene "
+              f"({last['samples']} samples, {last['rays']} rays per step)")
+    line = {"impl": "reference", "metric": "Mrays/s (primary+shadow)", "value": v, "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[name], "timing": "bounded CPU sample per step"},
+            "msamples_s": sum(x["msamples_s"] for x in vals) / len(vals),
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": last["threads"], "kind": "port", "sample": sample,
+                             "note": "restated reference CPU path (oracle/); the Rust reference cannot be built here"},
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "host_build_s": build_s}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("PSY_BENCH_WORKLOAD", "C5"), choices=sorted(WORKLOADS))
+    ap.add_argument("--pool", type=int, default=4 << 20, help="path-pool size (paths in flight per GPU)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--counter-spp", type=int, default=8)
+    ap.add_argument("--spp", type=int, default=0, help="override spp (profiling runs only; not the headline config)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        print(f"note: warmup {args.warmup} < 3 breaks the timing rules; use only for smoke runs", file=sys.stderr)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    g.build()
+    from psychopath_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the render core has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    name = args.workload
+    kw = WORKLOADS[name]
+    if args.spp:
+        kw["spp"] = args.spp
+        WORKLOAD_DESC[name] += f" [spp overridden to {args.spp}]"
+    spp, seed = kw["spp"], kw["seed"]
+    scene, build_s = build_scene(name)
+    t0 = time.time()
+    r = api.Renderer(scene, device=local_rank)
+    upload_s = time.time() - t0
+    rx, ry = scene.resolution
+
+    dev_ptr, n_floats = r.device_image()
+
+    class _Wrap:
+        __cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (dev_ptr, False), "version": 2}
+
+    image_t = torch.as_tensor(_Wrap(), device=torch.device("cuda", local_rank))
+    lat = torch.zeros(1, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        st = r.render_shard(rank, world, max_samples_per_bucket=args.pool) if world > 1 else \
+            r.render(max_samples_per_bucket=args.pool, device_resident_only=True)[1]
+        if world > 1:
+            dist.reduce(image_t, dst=0, op=dist.ReduceOp.SUM)  # tiles are disjoint, the rest is zero
+        return st
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rays = 0
+    launches = 0
+    trace_ms = 0.0
+    trace_launches = 0
+    stage = {"generate_ms": 0.0, "trace_ms": 0.0, "shade_ms": 0.0, "film_ms": 0.0}
+    barrier()
+    e0.record()
+    tw0 = time.perf_counter()
+    for _ in range(args.steps):
+        st = step()
+        rays += int(st["ray_count"])
+        launches += int(st["kernel_launches"])
+        ms, nl = r.last_trace_timing()
+        trace_ms += ms
+        trace_launches += nl
+        stage["generate_ms"] += st["initial_ray_generation_time"] * 1e3 / args.steps
+        stage["trace_ms"] += st["trace_time"] * 1e3 / args.steps
+        stage["shade_ms"] += st["ray_generation_time"] * 1e3 / args.steps
+        stage["film_ms"] += st["sample_writing_time"] * 1e3 / args.steps
+    e1.record()
+    barrier()
+    wall_s = time.perf_counter() - tw0
+    # The library renders on its own stream and synchronises it before returning, so the torch events on
+    # the current stream bracket the same region as the wall clock; use the larger of the two.
+    dev_s = max(e0.elapsed_time(e1) * 1e-3, wall_s)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_s, float(rays), float(launches), trace_ms, float(trace_launches)], dtype=torch.float64,
+                     device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_s = float(tmax[0])
+        rays = int(tsum[1])
+        launches = int(tsum[2])
+    samples_per_step = rx * ry * spp
+    value = rays / dev_s / 1e6
+    msamples = samples_per_step * args.steps / dev_s / 1e6
+
+    # ---- end-to-end through the C ABI with host buffers (rank-local; N=1 figure is the headline) ----
+    e2e = None
+    if world == 1:
+        def e2e_step():
+            rr = api.Renderer(scene, device=local_rank)      # H2D: the whole scene description
+            img, st2 = rr.render(max_samples_per_bucket=args.pool)  # D2H: the finished image
+            rr.close()
+            return img, st2
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e_rays = 0
+        n_e2e = max(1, min(args.steps, 2))
+        for _ in range(n_e2e):
+            img, st2 = e2e_step()
+            e_rays += int(st2["ray_count"])
+        torch.cuda.synchronize()
+        e_s = time.perf_counter() - t0
+        e2e = {"value": e_rays / e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(scene.host_bytes()),
+               "d2h_bytes_per_step": int(rx * ry * 12), "steps": n_e2e, "ms_per_step": e_s / n_e2e * 1e3,
+               "image_mean_xyz": [float(x) for x in img.reshape(-1, 3).mean(axis=0)]}
+
+    # ---- roofline of k_trace: visit counts from the counters build at reduced spp (per-ray averages) ----
+    roofline = None
+    cpu = None
+    if rank == 0:
+        pk, pk_kind = peaks()
+        _, cst = r.render(max_samples_per_bucket=args.pool, spp=min(args.counter_spp, spp), counters=True,
+                          device_resident_only=True)
+        b_ray, per_ray = algorithmic_bytes_per_ray(cst, keys_xform=1)
+        my_rays = int(t[1])
+        achieved = (my_rays * b_ray) / max(float(t[3]) * 1e-3, 1e-12) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+                    "bytes_per_ray": b_ray, "per_ray": per_ray,
+                    "trace_ms_per_step": float(t[3]) / args.steps, "trace_launches_per_step": float(t[4]) / args.steps,
+                    "trace_share_of_step": float(t[3]) * 1e-3 / dev_s,
+                    "roofline_mrays_s": pk["hbm_gbs"] * 1e9 / b_ray / 1e6,
+                    "note": "visit counts measured by the counters build at %d spp" % min(args.counter_spp, spp)}
+        if world == 1 and not args.no_cpu_baseline:
+            c = cpu_sample(scene, spp, seed, target_s=15.0)
+            cpu = {"value": c["mrays_s"], "unit": "Mrays/s", "cores": c["threads"], "kind": "port",
+                   "msamples_s": c["msamples_s"], "seconds": c["seconds"],
+                   "sample": f"{c['buckets']} Hilbert-ordered 4x4-pixel buckets x {spp} spp of the same scene "
+                             f"({c['samples']} samples, {c['rays']} rays)"}
+
+    if rank == 0:
+        line = {"metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD_DESC[name], "resolution": [rx, ry], "spp": spp, "seed": seed,
+                           "paths_in_flight": args.pool, "parallelism": f"tiles x{world}",
+                           "l2": "working set (path pool %d MB + scene) exceeds the 126 MB L2" % (args.pool * 216 >> 20)},
+                "msamples_s": msamples, "rays_per_step": rays / args.steps, "samples_per_step": samples_per_step,
+                "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+                "stage_ms_per_step_rank0": stage, "host_build_s": build_s, "upload_s": upload_s}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
