@@ -494,9 +494,14 @@ PSY_DEV void flip_normals(V3 inc, V3 nor, V3 nor_g, V3& nn, V3& fng) {
         fng = -nor_g;
     }
 }
+// KIND is the closure kind when the caller knows it at compile time (the shade kernels are
+// specialised per closure class), or CLOSURE_ANY to branch on cl.kind.
+constexpr uint32_t CLOSURE_ANY = 0xFFu;
+#define PSY_KIND_IS(K) ((KIND == CLOSURE_ANY) ? (cl.kind == (K)) : (KIND == (K)))
+template <uint32_t KIND>
 __device__ __noinline__ void closure_evaluate(const DScene& S, const Closure& cl, V3 inc, V3 out, V3 nor, V3 nor_g,
                                               float wl, V4& filter, float& pdf) {
-    if (cl.kind == PSY_SHADER_LAMBERT) {
+    if (PSY_KIND_IS(PSY_SHADER_LAMBERT)) {
         V3 nn, fng;
         flip_normals(inc, nor, nor_g, nn, fng);
         if (dot(fng, out) >= 0.0f) {
@@ -507,7 +512,7 @@ __device__ __noinline__ void closure_evaluate(const DScene& S, const Closure& cl
             filter = splat4(0.0f);
             pdf = 0.0f;
         }
-    } else if (cl.kind == PSY_SHADER_GGX) {
+    } else if (PSY_KIND_IS(PSY_SHADER_GGX)) {
         V3 aa = -normalized(inc);
         V3 bb = normalized(out);
         V3 hh = normalized(aa + bb);
@@ -543,9 +548,10 @@ __device__ __noinline__ void closure_evaluate(const DScene& S, const Closure& cl
         pdf = 1.0f;
     }
 }
+template <uint32_t KIND>
 PSY_DEV void closure_sample(const DScene& S, const Closure& cl, V3 inc, V3 nor, V3 nor_g, float u, float v, float wl,
                             V3& dir, V4& filter, float& pdf) {
-    if (cl.kind == PSY_SHADER_LAMBERT) {
+    if (PSY_KIND_IS(PSY_SHADER_LAMBERT)) {
         V3 nn, fng;
         flip_normals(inc, nor, nor_g, nn, fng);
         V3 d = cosine_sample_hemisphere(u, v);
@@ -559,7 +565,7 @@ PSY_DEV void closure_sample(const DScene& S, const Closure& cl, V3 inc, V3 nor, 
             filter = splat4(0.0f);
             pdf = 0.0f;
         }
-    } else if (cl.kind == PSY_SHADER_GGX) {
+    } else if (PSY_KIND_IS(PSY_SHADER_GGX)) {
         V3 nn, fng;
         flip_normals(inc, nor, nor_g, nn, fng);
         float theta_cos = half_theta_sample(u, cl.roughness);
@@ -570,7 +576,7 @@ PSY_DEV void closure_sample(const DScene& S, const Closure& cl, V3 inc, V3 nor, 
         V3 out = inc - (half_dir * 2.0f * dot(inc, half_dir));
         dir = out;
         if (dot(fng, out) >= 0.0f) {
-            closure_evaluate(S, cl, inc, out, nor, nor_g, wl, filter, pdf);
+            closure_evaluate<KIND>(S, cl, inc, out, nor, nor_g, wl, filter, pdf);
         } else {
             filter = splat4(0.0f);
             pdf = 0.0f;
@@ -597,9 +603,10 @@ PSY_DEV float sphere_lambert(float nlcos, float rcos) {
     if (nl < (PSY_H_PI + r)) return (g + h) * PSY_INV_PI;
     return 0.0f;
 }
+template <uint32_t KIND>
 PSY_DEV float closure_estimate_sphere(const Closure& cl, V3 inc, V3 to_light_center, float light_radius_squared, V3 nor,
                                       V3 nor_g) {
-    if (cl.kind == PSY_SHADER_LAMBERT) {
+    if (PSY_KIND_IS(PSY_SHADER_LAMBERT)) {
         float dist2 = length2(to_light_center);
         if (dist2 <= light_radius_squared) return rmin(light_radius_squared / dist2, 4.0f);
         float sin_theta_max2 = rmin(light_radius_squared / dist2, 1.0f);
@@ -608,7 +615,7 @@ PSY_DEV float closure_estimate_sphere(const Closure& cl, V3 inc, V3 to_light_cen
         V3 nn = dot(nor_g, inc) <= 0.0f ? normalized(nor) : -normalized(nor);
         float cos_nv = rmin(rmax(dot(nn, v), -1.0f), 1.0f);
         return sphere_lambert(cos_nv, cos_theta_max);
-    } else if (cl.kind == PSY_SHADER_GGX) {
+    } else if (PSY_KIND_IS(PSY_SHADER_GGX)) {
         float dist2 = length2(to_light_center);
         float sin_theta_max2 = rmin(light_radius_squared / dist2, 1.0f);
         float cos_theta_max = sqrtf(1.0f - sin_theta_max2);
@@ -782,6 +789,7 @@ struct LightSample {
 PSY_DEV V3 bbv(const float* p) { return mk3(p[0], p[1], p[2]); }
 
 // LightTree::select (light_tree.rs:135-201)
+template <uint32_t KIND>
 PSY_DEV bool light_tree_select(const DScene& S, const PsyAssembly& a, V3 inc, V3 pos, V3 nor, V3 nor_g,
                                const Closure& sc, float time, float n, uint32_t& light_i, float& sel_pdf,
                                float& whittled_n) {
@@ -811,7 +819,7 @@ PSY_DEV bool light_tree_select(const DScene& S, const PsyAssembly& a, V3 inc, V3
                 V3 dd = center - pos;
                 float r2 = length2(bmax - bmin) * 0.25f;
                 float inv_surface_area = 1.0f / r2;
-                float approx_contrib = closure_estimate_sphere(sc, inc, dd, r2, nor, nor_g);
+                float approx_contrib = closure_estimate_sphere<KIND>(sc, inc, dd, r2, nor, nor_g);
                 p = nd.energy * inv_surface_area * approx_contrib;
                 total += p;
             }
@@ -959,6 +967,7 @@ PSY_DEV float distant_energy(const DScene& S, const PsyDistantLight& l) {
 
 // Scene::sample_lights + Assembly::sample_lights, recursion unrolled into a loop
 // (scene/mod.rs:28-99, scene/assembly.rs:46-140)
+template <uint32_t KIND>
 __device__ __noinline__ void sample_lights(const DScene& S, float n, float u, float v, float wl, float time,
                                            const Isect& intr, LightSample& out) {
     out.kind = 0;
@@ -1029,7 +1038,7 @@ __device__ __noinline__ void sample_lights(const DScene& S, float n, float u, fl
         Xf sel_xform = have_parent ? path_xform(S, S.paths[cur_path], time) : xf_identity();
         uint32_t light_i;
         float sel_pdf, whittled_n;
-        if (!light_tree_select(S, a, xf_vector(sel_xform, intr.incoming), xf_point(sel_xform, intr.pos),
+        if (!light_tree_select<KIND>(S, a, xf_vector(sel_xform, intr.incoming), xf_point(sel_xform, intr.pos),
                                xf_normal(sel_xform, intr.nor), xf_normal(sel_xform, intr.nor_g), intr.closure, time, nn,
                                light_i, sel_pdf, whittled_n))
             return;

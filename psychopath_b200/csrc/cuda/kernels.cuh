@@ -42,6 +42,19 @@ struct Bucket {
     uint32_t x, y, w, h, spp, seed;
 };
 
+// Shading classes: k_trace sorts the paths of a wave into one queue per class so that the warps
+// of the shade kernels run one code path (Laine et al.'s wavefront formulation, here on the
+// reference's closure / event kinds).
+constexpr int SHADE_SIMPLE = 0;   // shadow-ray result, or a camera/bounce ray that missed
+constexpr int SHADE_EMIT = 1;     // hit an emitter (Emit closure) or light geometry
+constexpr int SHADE_LAMBERT = 2;  // surface hit, Lambert closure
+constexpr int SHADE_GGX = 3;      // surface hit, GGX closure
+constexpr int SHADE_CLASSES = 4;
+struct ShadeQueues {
+    uint32_t* q[SHADE_CLASSES];  // path slots per class
+    uint32_t* count;             // SHADE_CLASSES counters of the current wave
+};
+
 // Camera::generate_ray (camera.rs:74-102)
 PSY_DEV void camera_ray(const DScene& S, float x, float y, float time, float u, float v, V3& orig, V3& dir) {
     Xf transform = lerp_slice_xf(S.cam_xforms, S.n_cam_xforms, time);
@@ -95,7 +108,7 @@ __global__ void __launch_bounds__(256) k_generate(DScene S, PathPool P, Bucket b
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace(DScene S, PathPool P, const uint32_t* __restrict__ active,
                                                const uint32_t* __restrict__ count, uint32_t* fetch,
-                                               TraceCounters* counters) {
+                                               TraceCounters* counters, ShadeQueues Q) {
     const uint32_t n = *count;
     const uint32_t lane = threadIdx.x & 31u;
     TraceCounters cnt;
@@ -106,20 +119,44 @@ __global__ void __launch_bounds__(128) k_trace(DScene S, PathPool P, const uint3
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
         uint32_t i = base + lane;
+        uint32_t slot = 0;
+        int cls = -1;
         if (i < n) {
-            uint32_t slot = active[i];
+            slot = active[i];
             float4 ro = P.ray_o[slot], rd = P.ray_d[slot];
             RayIn ray;
             ray.orig = mk3(ro.x, ro.y, ro.z);
             ray.dir = mk3(rd.x, rd.y, rd.z);
             ray.time = ro.w;
             ray.max_t = rd.w;
-            ray.occlusion = (P.flags[slot] & F_OCCLUSION) != 0u;
+            const uint32_t flags = P.flags[slot];
+            ray.occlusion = (flags & F_OCCLUSION) != 0u;
             HitRec hit;
             trace_ray<COUNT>(S, ray, hit, cnt);
             uint4* hp = reinterpret_cast<uint4*>(P.hits + slot);
             hp[0] = make_uint4(hit.kind, __float_as_uint(hit.t), hit.prim, hit.path);
             hp[1] = make_uint4(__float_as_uint(hit.b0), __float_as_uint(hit.b1), __float_as_uint(hit.b2), 0u);
+            // shading class of this path for the next stage (see k_shade)
+            if (ray.occlusion || hit.kind == PSY_HIT_MISS) {
+                cls = SHADE_SIMPLE;
+            } else if (hit.kind != PSY_HIT_TRIANGLE) {
+                cls = SHADE_EMIT;
+            } else {
+                uint32_t sh = S.instances[S.paths[hit.path].inst].shader_index;
+                uint32_t kind = sh == PSY_NONE ? (uint32_t)PSY_SHADER_EMIT : S.shaders[sh].kind;
+                cls = kind == PSY_SHADER_LAMBERT ? SHADE_LAMBERT : (kind == PSY_SHADER_GGX ? SHADE_GGX : SHADE_EMIT);
+            }
+        }
+        // one queue per shading class: warp ballot + popc prefix + one atomic per warp and class
+#pragma unroll
+        for (int c = 0; c < SHADE_CLASSES; ++c) {
+            uint32_t mask = __ballot_sync(0xffffffffu, cls == c);
+            if (mask) {
+                uint32_t qb = 0;
+                if (lane == 0) qb = atomicAdd(Q.count + c, __popc(mask));
+                qb = __shfl_sync(0xffffffffu, qb, 0);
+                if (cls == c) Q.q[c][qb + __popc(mask & ((1u << lane) - 1u))] = slot;
+            }
         }
     }
     if (COUNT) {
@@ -190,47 +227,49 @@ __global__ void __launch_bounds__(128) k_trace_probe(DScene S, const PsyRay* __r
     }
 }
 
-// LightPath::next for one path; returns true when the path stays alive (a new ray was written).
+// LightPath::next for one path of shading class CLS; returns true when the path stays alive (a new
+// ray was written).  The class is decided by k_trace, so each instantiation only carries its own code:
+//   SHADE_SIMPLE   shadow-ray results and camera/bounce rays that missed (renderer.rs:659-689)
+//   SHADE_EMIT     hits on emitters and light geometry                    (renderer.rs:472-483)
+//   SHADE_LAMBERT / SHADE_GGX   surface hits: NEE + bounce                (renderer.rs:485-657)
+template <int CLS>
 PSY_DEV bool path_next(const DScene& S, const PathPool& P, uint32_t slot, const Bucket& b) {
     uint32_t flags = P.flags[slot];
-    uint32_t event = (flags & F_EVENT_MASK) >> F_EVENT_SHIFT;
-    const HitRec h = P.hits[slot];
+    const uint32_t event = (flags & F_EVENT_MASK) >> F_EVENT_SHIFT;
     float4 ro = P.ray_o[slot];
     const float time = ro.w;
     const float wl = P.wavelength[slot];
 
-    if (event == EV_SHADOW) {
-        // renderer.rs:673-689
-        if (h.kind == PSY_HIT_MISS) P.color[slot] = to_f4(from_f4(P.color[slot]) + from_f4(P.pending[slot]));
-        if (flags & F_HAS_NEXT) {
-            float4 o = P.nb_o[slot], d = P.nb_d[slot];
-            P.ray_o[slot] = make_float4(o.x, o.y, o.z, time);
-            P.ray_d[slot] = make_float4(d.x, d.y, d.z, CUDART_INF_F);
-            P.light_atten[slot] = to_f4(from_f4(P.light_atten[slot]) * from_f4(P.next_atten[slot]));
-            flags = (flags & ~(F_EVENT_MASK | F_OCCLUSION)) | (EV_BOUNCE << F_EVENT_SHIFT);
-            P.flags[slot] = flags;
-            return true;
+    if (CLS == SHADE_SIMPLE) {
+        if (event == EV_SHADOW) {
+            const uint32_t hit_kind = P.hits[slot].kind;
+            if (hit_kind == PSY_HIT_MISS) P.color[slot] = to_f4(from_f4(P.color[slot]) + from_f4(P.pending[slot]));
+            if (flags & F_HAS_NEXT) {
+                float4 o = P.nb_o[slot], d = P.nb_d[slot];
+                P.ray_o[slot] = make_float4(o.x, o.y, o.z, time);
+                P.ray_d[slot] = make_float4(d.x, d.y, d.z, CUDART_INF_F);
+                P.light_atten[slot] = to_f4(from_f4(P.light_atten[slot]) * from_f4(P.next_atten[slot]));
+                flags = (flags & ~(F_EVENT_MASK | F_OCCLUSION)) | (EV_BOUNCE << F_EVENT_SHIFT);
+                P.flags[slot] = flags;
+                return true;
+            }
+            return false;
         }
+        // background
+        V4 bg = color_to_spectral(S, S.background, wl);
+        P.color[slot] = to_f4(from_f4(P.color[slot]) + ((bg * from_f4(P.light_atten[slot])) / P.closure_pdf[slot]));
         return false;
     }
 
+    const HitRec h = P.hits[slot];
     float4 rd = P.ray_d[slot];
     V3 orig = mk3(ro.x, ro.y, ro.z), dir = mk3(rd.x, rd.y, rd.z);
     V4 light_attenuation = from_f4(P.light_atten[slot]);
     float closure_sample_pdf = P.closure_pdf[slot];
-
-    bool is_hit = h.kind == PSY_HIT_TRIANGLE || h.kind == PSY_HIT_SPHERE_LIGHT || h.kind == PSY_HIT_RECT_LIGHT;
-    if (!is_hit) {
-        // background (renderer.rs:659-667)
-        V4 bg = color_to_spectral(S, S.background, wl);
-        P.color[slot] = to_f4(from_f4(P.color[slot]) + ((bg * light_attenuation) / closure_sample_pdf));
-        return false;
-    }
     Isect is;
     finalize_hit(S, h, orig, dir, time, is);
 
-    if (is.closure.kind == PSY_SHADER_EMIT) {
-        // renderer.rs:472-483
+    if (CLS == SHADE_EMIT) {
         V4 c = color_to_spectral(S, is.closure.color, wl);
         V4 col = from_f4(P.color[slot]);
         if (event == EV_CAMERA) {
@@ -242,6 +281,7 @@ PSY_DEV bool path_next(const DScene& S, const PathPool& P, uint32_t slot, const 
         P.color[slot] = to_f4(col);
         return false;
     }
+    constexpr uint32_t KIND = CLS == SHADE_LAMBERT ? (uint32_t)PSY_SHADER_LAMBERT : (uint32_t)PSY_SHADER_GGX;
     light_attenuation = light_attenuation / closure_sample_pdf;
 
     // light sample (renderer.rs:488-596)
@@ -252,7 +292,7 @@ PSY_DEV bool path_next(const DScene& S, const PathPool& P, uint32_t slot, const 
     float s4[4];
     get_sample_4d(si, 0, px, py, sseed, s4);
     LightSample li;
-    sample_lights(S, s4[0], s4[1], s4[2], wl, time, is, li);
+    sample_lights<KIND>(S, s4[0], s4[1], s4[2], wl, time, is, li);
     bool found_light = false;
     if (!(li.kind == 0 || li.pdf <= 0.0f || li.selection_pdf <= 0.0f)) {
         V4 attenuation;
@@ -260,15 +300,13 @@ PSY_DEV bool path_next(const DScene& S, const PathPool& P, uint32_t slot, const 
         V3 so, sd;
         float smax;
         V3 ng = normalized(is.nor_g);
+        V3 ldir = li.kind == 1 ? li.direction : li.pos - is.pos;
+        closure_evaluate<KIND>(S, is.closure, dir, ldir, is.nor, is.nor_g, wl, attenuation, closure_pdf);
+        so = robust_ray_origin(is.pos, is.pos_err, ng, ldir);
         if (li.kind == 1) {
-            closure_evaluate(S, is.closure, dir, li.direction, is.nor, is.nor_g, wl, attenuation, closure_pdf);
-            so = robust_ray_origin(is.pos, is.pos_err, ng, li.direction);
             sd = li.direction;
             smax = CUDART_INF_F;
         } else {
-            V3 ldir = li.pos - is.pos;
-            closure_evaluate(S, is.closure, dir, ldir, is.nor, is.nor_g, wl, attenuation, closure_pdf);
-            so = robust_ray_origin(is.pos, is.pos_err, ng, ldir);
             V3 offset_end = robust_ray_origin(li.pos, li.err, normalized(li.nor), -ldir);
             sd = offset_end - so;
             smax = 1.0f;
@@ -296,7 +334,7 @@ PSY_DEV bool path_next(const DScene& S, const PathPool& P, uint32_t slot, const 
         V3 bdir;
         V4 filter;
         float pdf;
-        closure_sample(S, is.closure, is.incoming, is.nor, is.nor_g, b4[0], b4[1], wl, bdir, filter, pdf);
+        closure_sample<KIND>(S, is.closure, is.incoming, is.nor, is.nor_g, b4[0], b4[1], wl, bdir, filter, pdf);
         if ((pdf > 0.0f) && (max_element4(filter) > 0.0f)) {
             next_atten = filter;
             closure_sample_pdf = pdf;
@@ -333,18 +371,20 @@ PSY_DEV bool path_next(const DScene& S, const PathPool& P, uint32_t slot, const 
     return false;
 }
 
-__global__ void __launch_bounds__(128) k_shade(DScene S, PathPool P, Bucket b, const uint32_t* __restrict__ active_in,
-                                               const uint32_t* __restrict__ count_in, uint32_t* active_out,
+// One launch per shading class; survivors of all classes are appended to the next wave's live list.
+template <int CLS>
+__global__ void __launch_bounds__(128) k_shade(DScene S, PathPool P, Bucket b, ShadeQueues Q, uint32_t* active_out,
                                                uint32_t* count_out) {
-    const uint32_t n = *count_in;
+    const uint32_t n = Q.count[CLS];
+    const uint32_t* __restrict__ queue = Q.q[CLS];
     const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
         uint32_t i = base + lane;
         bool alive = false;
         uint32_t slot = 0;
         if (i < n) {
-            slot = active_in[i];
-            alive = path_next(S, P, slot, b);
+            slot = queue[i];
+            alive = path_next<CLS>(S, P, slot, b);
         }
         // stream compaction: ballot + popc prefix + one atomic per warp (replaces the swap
         // compaction of renderer.rs:286-295)

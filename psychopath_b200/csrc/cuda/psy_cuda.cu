@@ -78,7 +78,7 @@ struct PsyScene {
     size_t pool_cap = 0;
     DevBuf pool_ray_o, pool_ray_d, pool_flags, pool_sseed, pool_wl, pool_cpdf, pool_nb_o, pool_nb_d, pool_next_atten,
         pool_light_atten, pool_pending, pool_color, pool_hits, active_a, active_b;
-    DevBuf counts, fetch, counters, image, bucket_out, samples_out;
+    DevBuf counts, fetch, qcounts, queues, counters, image, bucket_out, samples_out;
     size_t counts_cap = 0;
     std::vector<cudaEvent_t> events;
     size_t events_used = 0;
@@ -227,6 +227,7 @@ int32_t ensure_pool(PsyScene* sc, size_t n) {
     CK(sc->pool_hits.alloc(cap * sizeof(HitRec)));
     CK(sc->active_a.alloc(cap * 4));
     CK(sc->active_b.alloc(cap * 4));
+    CK(sc->queues.alloc(cap * 4 * SHADE_CLASSES));
     sc->pool_cap = cap;
     return PSY_OK;
 }
@@ -239,6 +240,7 @@ int32_t ensure_counts(PsyScene* sc, size_t n_buckets) {
     if (n_buckets <= sc->counts_cap) return PSY_OK;
     CK(sc->counts.alloc(n_buckets * COUNT_SLOTS * 4));
     CK(sc->fetch.alloc(n_buckets * COUNT_SLOTS * 4));
+    CK(sc->qcounts.alloc(n_buckets * COUNT_SLOTS * SHADE_CLASSES * 4));
     sc->counts_cap = n_buckets;
     return PSY_OK;
 }
@@ -281,18 +283,27 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
     *launches += 1;
     uint32_t trace_blocks = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 12);
     uint32_t shade_blocks = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 16);
+    ShadeQueues Q;
+    for (int c = 0; c < SHADE_CLASSES; ++c) Q.q[c] = sc->queues.as<uint32_t>() + (size_t)c * sc->pool_cap;
+    uint32_t* qcounts = sc->qcounts.as<uint32_t>() + bucket_index * COUNT_SLOTS * SHADE_CLASSES;
     for (int w = 0; w < WAVES; ++w) {
+        Q.count = qcounts + w * SHADE_CLASSES;
         stamp(ev ? &ev->trace : nullptr, true);
         if (counters)
             k_trace<true><<<trace_blocks, 128, 0, st>>>(sc->d, P, act[w & 1], counts + w, fetch + w,
-                                                        sc->counters.as<TraceCounters>());
+                                                        sc->counters.as<TraceCounters>(), Q);
         else
-            k_trace<false><<<trace_blocks, 128, 0, st>>>(sc->d, P, act[w & 1], counts + w, fetch + w, nullptr);
+            k_trace<false><<<trace_blocks, 128, 0, st>>>(sc->d, P, act[w & 1], counts + w, fetch + w, nullptr, Q);
         stamp(ev ? &ev->trace : nullptr, false);
         stamp(ev ? &ev->shade : nullptr, true);
-        k_shade<<<shade_blocks, 128, 0, st>>>(sc->d, P, b, act[w & 1], counts + w, act[(w + 1) & 1], counts + w + 1);
+        uint32_t* next_active = act[(w + 1) & 1];
+        uint32_t* next_count = counts + w + 1;
+        k_shade<SHADE_SIMPLE><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
+        k_shade<SHADE_EMIT><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
+        k_shade<SHADE_LAMBERT><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
+        k_shade<SHADE_GGX><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
         stamp(ev ? &ev->shade : nullptr, false);
-        *launches += 2;
+        *launches += 5;
     }
     stamp(ev ? &ev->film : nullptr, true);
     k_film<<<(b.w * b.h + 127) / 128, 128, 0, st>>>(P, b, out, stride, ox, oy, samples_out);
@@ -365,6 +376,7 @@ int32_t render_buckets(PsyScene* sc, const std::vector<Bucket>& jobs, bool count
     if (!jobs.empty()) {
         CK(cudaMemsetAsync(sc->counts.p, 0, jobs.size() * COUNT_SLOTS * 4, st));
         CK(cudaMemsetAsync(sc->fetch.p, 0, jobs.size() * COUNT_SLOTS * 4, st));
+        CK(cudaMemsetAsync(sc->qcounts.p, 0, jobs.size() * COUNT_SLOTS * SHADE_CLASSES * 4, st));
     }
     sc->events_used = 0;
     StageEvents ev;
@@ -773,6 +785,7 @@ static int32_t render_bucket_impl(PsyScene* sc, uint32_t x, uint32_t y, uint32_t
     if (rc) return rc;
     CK(cudaMemsetAsync(sc->counts.p, 0, COUNT_SLOTS * 4, st));
     CK(cudaMemsetAsync(sc->fetch.p, 0, COUNT_SLOTS * 4, st));
+    CK(cudaMemsetAsync(sc->qcounts.p, 0, COUNT_SLOTS * SHADE_CLASSES * 4, st));
     CK(sc->bucket_out.alloc((size_t)w * h * 3 * 4));
     if (samples_out) CK(sc->samples_out.alloc(n * 16));
     Bucket b{x, y, w, h, spp, seed};
