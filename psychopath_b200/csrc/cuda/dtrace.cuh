@@ -196,263 +196,5 @@ PSY_DEV void rect_corners(const Xf& space_inv, float w, float h, V3& p1, V3& p2,
     p4 = xf_point(space_inv, mk3(w * 0.5f, h * -0.5f, 0.0f));
 }
 
-template <bool COUNT>
-PSY_DEV void trace_ray(const DScene& S, const RayIn& ray, HitRec& hit, TraceCounters& cnt) {
-    hit.kind = PSY_HIT_MISS;
-    hit.t = 0.0f;
-    hit.prim = 0;
-    hit.path = 0;
-    hit.b0 = hit.b1 = hit.b2 = 0.0f;
-    hit.pad = 0;
-
-    float max_t = ray.max_t;
-    const RayTriPre pre = tri_precompute(ray.dir);
-
-    // current space
-    V3 orig_local, dir_inv_local;
-    {
-        Xf ident = xf_identity();  // tracer.rs:66-69: update_local(i, identity), evaluated literally
-        orig_local = xf_point(ident, ray.orig);
-        dir_inv_local = recip3(xf_vector(ident, ray.dir));
-    }
-    // assembly-level context
-    uint32_t cur_asm = S.root_assembly;
-    uint32_t path_base = 0;
-    uint32_t active_path = PSY_NONE;  // path whose composed transform is the current space
-    uint32_t ctx_asm[TRACE_MAX_NEST], ctx_base[TRACE_MAX_NEST], ctx_active[TRACE_MAX_NEST];
-    int ctx_n = 0;
-    // mesh-level context
-    bool in_mesh = false;
-    uint32_t mesh_parent_active = PSY_NONE;
-    uint32_t mesh_path = 0;
-    bool mesh_own_xform = false;
-    bool space_empty = true;
-    DMesh mesh;
-    mesh.root = PSY_NONE, mesh.tri_base = 0, mesh.tri_count = 0, mesh.n_keys = 1, mesh.tv_base = 0, mesh.vert_base = 0,
-    mesh.has_normals = 0, mesh.pad = 0;
-    Xf mat_space = xf_identity();
-
-    uint32_t stack[TRACE_STACK_SIZE];
-    int sp = 0;
-    {
-        uint32_t root = S.assemblies[cur_asm].root;
-        if (root != PSY_NONE) stack[sp++] = root;
-    }
-
-    while (sp > 0) {
-        uint32_t ref = stack[--sp];
-        if (ref == MARK_POP_MESH) {
-            in_mesh = false;
-            active_path = mesh_parent_active;
-            if (mesh_own_xform) {
-                Xf x = active_path == PSY_NONE ? xf_identity() : path_xform(S, S.paths[active_path], ray.time);
-                orig_local = xf_point(x, ray.orig);
-                dir_inv_local = recip3(xf_vector(x, ray.dir));
-            }
-            continue;
-        }
-        if (ref == MARK_POP_ASM) {
-            --ctx_n;
-            bool own = S.instances[S.paths[active_path].inst].xform_count > 0;
-            cur_asm = ctx_asm[ctx_n];
-            path_base = ctx_base[ctx_n];
-            active_path = ctx_active[ctx_n];
-            if (own) {
-                Xf x = active_path == PSY_NONE ? xf_identity() : path_xform(S, S.paths[active_path], ray.time);
-                orig_local = xf_point(x, ray.orig);
-                dir_inv_local = recip3(xf_vector(x, ray.dir));
-            }
-            continue;
-        }
-        if (ref & PSY_CHILD_LEAF_BIT) {
-            uint32_t start = PSY_CHILD_LEAF_START(ref);
-            uint32_t count = PSY_CHILD_LEAF_COUNT(ref);
-            if (in_mesh) {
-                // ---- triangle leaf (triangle_mesh.rs:174-262)
-                for (uint32_t ti = start; ti < start + count; ++ti) {
-                    V3 p0, p1, p2;
-                    load_tri(S, mesh, ti, ray.time, p0, p1, p2);
-                    if (!space_empty) {
-                        p0 = xf_point(mat_space, p0);
-                        p1 = xf_point(mat_space, p1);
-                        p2 = xf_point(mat_space, p2);
-                    }
-                    if (COUNT) cnt.tri_tests += 1;
-                    float t, b0, b1, b2;
-                    if (tri_intersect(ray.orig, pre, max_t, p0, p1, p2, t, b0, b1, b2)) {
-                        if (ray.occlusion) {
-                            hit.kind = PSY_HIT_OCCLUDED;
-                            return;
-                        }
-                        max_t = t;
-                        hit.kind = PSY_HIT_TRIANGLE;
-                        hit.t = t;
-                        hit.prim = ti;
-                        hit.path = mesh_path;
-                        hit.b0 = b0, hit.b1 = b1, hit.b2 = b2;
-                    }
-                }
-            } else {
-                // ---- instance (tracer.rs:94-149); assembly leaves hold exactly one instance
-                const PsyInstance inst = S.instances[start];
-                uint32_t p = path_base + (start - S.assemblies[cur_asm].instance_base);
-                const DPath P = S.paths[p];
-                bool own = inst.xform_count > 0;
-                if (COUNT) cnt.instance_visits += 1;
-                if (inst.kind == PSY_INSTANCE_OBJECT) {
-                    const PsyObject obj = S.objects[inst.data_index];
-                    if (obj.kind == PSY_OBJECT_MESH) {
-                        mesh = S.meshes[obj.index];
-                        if (mesh.root == PSY_NONE) continue;
-                        mesh_parent_active = active_path;
-                        mesh_own_xform = own;
-                        mesh_path = p;
-                        active_path = p;
-                        space_empty = P.xf_count == 0;
-                        if (own) {
-                            Xf x = path_xform(S, P, ray.time);
-                            orig_local = xf_point(x, ray.orig);
-                            dir_inv_local = recip3(xf_vector(x, ray.dir));
-                        }
-                        if (!space_empty) mat_space = path_mat_space(S, P, p, ray.time);
-                        in_mesh = true;
-                        stack[sp++] = MARK_POP_MESH;
-                        stack[sp++] = mesh.root;
-                    } else {
-                        const PsyLight l = S.lights[obj.index];
-                        Xf xform = path_xform(S, P, ray.time);
-                        if (l.kind == PSY_LIGHT_SPHERE) {
-                            V3 ol = own ? xf_point(xform, ray.orig) : orig_local;
-                            float t;
-                            if (sphere_light_hit(S, l, xform, ol, ray.dir, ray.time, max_t, t)) {
-                                if (ray.occlusion) {
-                                    hit.kind = PSY_HIT_OCCLUDED;
-                                    return;
-                                }
-                                max_t = t;
-                                hit.kind = PSY_HIT_SPHERE_LIGHT;
-                                hit.t = t;
-                                hit.prim = 0;
-                                hit.path = p;
-                                hit.b0 = hit.b1 = hit.b2 = 0.0f;
-                            }
-                        } else {
-                            float w, h;
-                            rect_dims(S, l, ray.time, w, h);
-                            Xf space_inv = xf_inverse(xform);
-                            V3 p1, p2, p3, p4;
-                            rect_corners(space_inv, w, h, p1, p2, p3, p4);
-#pragma unroll 1
-                            for (int k = 0; k < 2; ++k) {
-                                V3 a = k == 0 ? p1 : p3, b = k == 0 ? p2 : p4, c = k == 0 ? p3 : p1;
-                                float t, b0, b1, b2;
-                                if (COUNT) cnt.tri_tests += 1;
-                                if (tri_intersect(ray.orig, pre, max_t, a, b, c, t, b0, b1, b2)) {
-                                    if (t < max_t) {
-                                        if (ray.occlusion) {
-                                            hit.kind = PSY_HIT_OCCLUDED;
-                                            return;
-                                        }
-                                        max_t = t;
-                                        hit.kind = PSY_HIT_RECT_LIGHT;
-                                        hit.t = t;
-                                        hit.prim = (uint32_t)k;
-                                        hit.path = p;
-                                        hit.b0 = b0, hit.b1 = b1, hit.b2 = b2;
-                                        break;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                } else {
-                    // sub-assembly (tracer.rs:125-127)
-                    const PsyAssembly sub = S.assemblies[inst.data_index];
-                    if (sub.root == PSY_NONE || ctx_n >= TRACE_MAX_NEST) continue;
-                    ctx_asm[ctx_n] = cur_asm;
-                    ctx_base[ctx_n] = path_base;
-                    ctx_active[ctx_n] = active_path;
-                    ++ctx_n;
-                    cur_asm = inst.data_index;
-                    path_base = P.child_base;
-                    active_path = p;
-                    if (own) {
-                        Xf x = path_xform(S, P, ray.time);
-                        orig_local = xf_point(x, ray.orig);
-                        dir_inv_local = recip3(xf_vector(x, ray.dir));
-                    }
-                    stack[sp++] = MARK_POP_ASM;
-                    stack[sp++] = sub.root;
-                }
-            }
-            continue;
-        }
-
-        // ---- internal node (bvh4.rs:118-166, bbox4.rs:63-97)
-        const uint4* np = S.nodes + (size_t)ref * 8u;
-        const uint4 child = __ldg(np);
-        const uint4 meta = __ldg(np + 1);  // traversal_code, n_keys, key_base, n_children
-        float4 bx0, bx1, by0, by1, bz0, bz1;
-        if (meta.y == 1u) {
-            const float4* bp = reinterpret_cast<const float4*>(np + 2);
-            bx0 = __ldg(bp), bx1 = __ldg(bp + 1), by0 = __ldg(bp + 2), by1 = __ldg(bp + 3), bz0 = __ldg(bp + 4),
-            bz1 = __ldg(bp + 5);
-        } else {
-            if (COUNT) cnt.motion_node_visits += 1;
-            uint32_t i1;
-            float a2;
-            bool blend = lerp_slice_keys(meta.y, ray.time, i1, a2);
-            const float4* k0 = S.motion_bounds + (size_t)(meta.z + i1) * 6u;
-            bx0 = __ldg(k0), bx1 = __ldg(k0 + 1), by0 = __ldg(k0 + 2), by1 = __ldg(k0 + 3), bz0 = __ldg(k0 + 4),
-            bz1 = __ldg(k0 + 5);
-            if (blend) {
-                const float4* k1 = k0 + 6;
-                float ia = 1.0f - a2;
-#define PSY_LERP4(A, B)                                                                                    \
-    A = make_float4((A.x * ia) + (B.x * a2), (A.y * ia) + (B.y * a2), (A.z * ia) + (B.z * a2), (A.w * ia) + (B.w * a2))
-                float4 c0 = __ldg(k1), c1 = __ldg(k1 + 1), c2 = __ldg(k1 + 2), c3 = __ldg(k1 + 3), c4 = __ldg(k1 + 4),
-                       c5 = __ldg(k1 + 5);
-                PSY_LERP4(bx0, c0);
-                PSY_LERP4(bx1, c1);
-                PSY_LERP4(by0, c2);
-                PSY_LERP4(by1, c3);
-                PSY_LERP4(bz0, c4);
-                PSY_LERP4(bz1, c5);
-#undef PSY_LERP4
-            }
-        }
-        if (COUNT) cnt.node_visits += 1;
-        const float ADJ = 1.00000024f;
-        uint32_t hits = 0;
-#define PSY_SLAB(LANE, BIT)                                                                 \
-    {                                                                                       \
-        float t1x = (bx0.LANE - orig_local.x) * dir_inv_local.x;                            \
-        float t1y = (by0.LANE - orig_local.y) * dir_inv_local.y;                            \
-        float t1z = (bz0.LANE - orig_local.z) * dir_inv_local.z;                            \
-        float t2x = (bx1.LANE - orig_local.x) * dir_inv_local.x;                            \
-        float t2y = (by1.LANE - orig_local.y) * dir_inv_local.y;                            \
-        float t2z = (bz1.LANE - orig_local.z) * dir_inv_local.z;                            \
-        float fx = sse_max(t1x, t2x), fy = sse_max(t1y, t2y), fz = sse_max(t1z, t2z);       \
-        float nx = sse_min(t1x, t2x), ny = sse_min(t1y, t2y), nz = sse_min(t1z, t2z);       \
-        float far_t = sse_min(sse_min(fx, sse_min(fy, fz)) * ADJ, max_t);                   \
-        float near_t = sse_max(sse_max(nx, ny), sse_max(nz, 0.0f));                         \
-        if (near_t < far_t) hits |= (1u << BIT);                                            \
-    }
-        PSY_SLAB(x, 0)
-        PSY_SLAB(y, 1)
-        if (meta.w > 2u) PSY_SLAB(z, 2)
-        if (meta.w > 3u) PSY_SLAB(w, 3)
-#undef PSY_SLAB
-        if (hits) {
-            uint32_t order_code = c_traversal_table[ray_code(dir_inv_local)][meta.x];
-            const uint32_t ch[4] = {child.x, child.y, child.z, child.w};
-            for (int i = (int)meta.w; i > 0;) {
-                --i;
-                uint32_t child_i = (order_code >> (i * 2)) & 3u;
-                if (hits & (1u << child_i)) stack[sp++] = ch[child_i];
-            }
-        }
-    }
-}
 
 }  // namespace psyd

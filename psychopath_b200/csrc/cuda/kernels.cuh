@@ -10,6 +10,7 @@
 #include <math_constants.h>
 
 #include "dshade.cuh"
+#include "dtraverse.cuh"
 
 namespace psyd {
 
@@ -50,6 +51,13 @@ constexpr int SHADE_EMIT = 1;     // hit an emitter (Emit closure) or light geom
 constexpr int SHADE_LAMBERT = 2;  // surface hit, Lambert closure
 constexpr int SHADE_GGX = 3;      // surface hit, GGX closure
 constexpr int SHADE_CLASSES = 4;
+// Persistent trace kernel tuning: stack pops between two refill checks, idle lanes that trigger a refill
+struct TraceTuning {
+    int step_budget;  // default 24
+    int refill_min;   // idle lanes that trigger a refill; 32 = classic "fetch a full warp of rays when the warp is empty"
+    int leaf_min;     // parked leaves / instance entries that trigger their joint processing
+};
+
 struct ShadeQueues {
     uint32_t* q[SHADE_CLASSES];  // path slots per class
     uint32_t* count;             // SHADE_CLASSES counters of the current wave
@@ -106,38 +114,60 @@ __global__ void __launch_bounds__(256) k_generate(DScene S, PathPool P, Bucket b
 
 // Persistent trace kernel: warps fetch 32 rays at a time from a global counter.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace(DScene S, PathPool P, const uint32_t* __restrict__ active,
+#ifndef PSY_TRACE_MIN_BLOCKS
+#define PSY_TRACE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, PSY_TRACE_MIN_BLOCKS) k_trace(DScene S, PathPool P, const uint32_t* __restrict__ active,
                                                const uint32_t* __restrict__ count, uint32_t* fetch,
-                                               TraceCounters* counters, ShadeQueues Q) {
+                                               TraceCounters* counters, ShadeQueues Q, TraceTuning tune) {
     const uint32_t n = *count;
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t FULL = 0xffffffffu;
     TraceCounters cnt;
     cnt.node_visits = cnt.tri_tests = cnt.instance_visits = cnt.motion_node_visits = 0;
+    TraversalMem mem;
+    Traversal<COUNT> tr;
+    tr.attach(mem);
+    bool busy = false;       // this lane holds a ray
+    bool exhausted = false;  // warp-uniform: the global ray queue is empty
+    uint32_t slot = 0;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(fetch, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t i = base + lane;
-        uint32_t slot = 0;
+        // Lane refill: finished lanes take new rays as soon as tune.refill_min of them are idle, so a
+        // long ray does not hold 31 empty lanes hostage.
+        const uint32_t idle = __ballot_sync(FULL, !busy);
+        if (!exhausted && (idle == FULL || __popc(idle) >= tune.refill_min)) {
+            const uint32_t want = __popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(fetch, want);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + want >= n) exhausted = true;
+            if (!busy) {
+                uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < n) {
+                    slot = active[i];
+                    float4 ro = P.ray_o[slot], rd = P.ray_d[slot];
+                    RayIn ray;
+                    ray.orig = mk3(ro.x, ro.y, ro.z);
+                    ray.dir = mk3(rd.x, rd.y, rd.z);
+                    ray.time = ro.w;
+                    ray.max_t = rd.w;
+                    ray.occlusion = (P.flags[slot] & F_OCCLUSION) != 0u;
+                    tr.begin(S, ray);
+                    busy = true;
+                }
+            }
+        }
+        if (__ballot_sync(FULL, busy) == 0u) break;
+        tr.run_warp(S, tune.step_budget, exhausted ? 33 : tune.refill_min, tune.leaf_min, cnt);
         int cls = -1;
-        if (i < n) {
-            slot = active[i];
-            float4 ro = P.ray_o[slot], rd = P.ray_d[slot];
-            RayIn ray;
-            ray.orig = mk3(ro.x, ro.y, ro.z);
-            ray.dir = mk3(rd.x, rd.y, rd.z);
-            ray.time = ro.w;
-            ray.max_t = rd.w;
-            const uint32_t flags = P.flags[slot];
-            ray.occlusion = (flags & F_OCCLUSION) != 0u;
-            HitRec hit;
-            trace_ray<COUNT>(S, ray, hit, cnt);
+        if (busy && tr.done()) {
+            busy = false;
+            const HitRec& hit = tr.hit;
             uint4* hp = reinterpret_cast<uint4*>(P.hits + slot);
             hp[0] = make_uint4(hit.kind, __float_as_uint(hit.t), hit.prim, hit.path);
             hp[1] = make_uint4(__float_as_uint(hit.b0), __float_as_uint(hit.b1), __float_as_uint(hit.b2), 0u);
             // shading class of this path for the next stage (see k_shade)
-            if (ray.occlusion || hit.kind == PSY_HIT_MISS) {
+            if (tr.occlusion || hit.kind == PSY_HIT_MISS) {
                 cls = SHADE_SIMPLE;
             } else if (hit.kind != PSY_HIT_TRIANGLE) {
                 cls = SHADE_EMIT;
@@ -174,16 +204,24 @@ __global__ void __launch_bounds__(128) k_trace_probe(DScene S, const PsyRay* __r
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     TraceCounters cnt;
     cnt.node_visits = cnt.tri_tests = cnt.instance_visits = cnt.motion_node_visits = 0;
+    TraversalMem mem;
+    Traversal<COUNT> tr;
+    tr.attach(mem);
+    RayIn ray;
+    ray.orig = ray.dir = mk3(0, 0, 0);
+    ray.time = 0.0f, ray.max_t = 0.0f, ray.occlusion = false;
     if (i < n) {
         PsyRay r = rays[i];
-        RayIn ray;
         ray.orig = mk3(r.orig[0], r.orig[1], r.orig[2]);
         ray.dir = mk3(r.dir[0], r.dir[1], r.dir[2]);
         ray.time = r.time;
         ray.max_t = r.max_t;
         ray.occlusion = (r.flags & PSY_RAY_OCCLUSION) != 0u;
-        HitRec h;
-        trace_ray<COUNT>(S, ray, h, cnt);
+        tr.begin(S, ray);
+    }
+    tr.run_warp(S, 1 << 30, 33, 12, cnt);  // every lane of the warp takes part (lanes past n hold no ray)
+    if (i < n) {
+        const HitRec h = tr.hit;
         PsyHit o;
         o.kind = h.kind;
         o.t = h.t;

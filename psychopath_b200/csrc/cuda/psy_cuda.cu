@@ -284,6 +284,13 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
     uint32_t trace_blocks = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 12);
     uint32_t shade_blocks = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 16);
     ShadeQueues Q;
+    static const TraceTuning tune = [] {
+        TraceTuning t{64, 8, 8};  // measured best on the C4 scene (profiles/README.md)
+        if (const char* e = getenv("PSY_TRACE_LEAFMIN")) t.leaf_min = atoi(e);
+        if (const char* e = getenv("PSY_TRACE_BUDGET")) t.step_budget = atoi(e);
+        if (const char* e = getenv("PSY_TRACE_REFILL")) t.refill_min = atoi(e);
+        return t;
+    }();
     for (int c = 0; c < SHADE_CLASSES; ++c) Q.q[c] = sc->queues.as<uint32_t>() + (size_t)c * sc->pool_cap;
     uint32_t* qcounts = sc->qcounts.as<uint32_t>() + bucket_index * COUNT_SLOTS * SHADE_CLASSES;
     for (int w = 0; w < WAVES; ++w) {
@@ -291,9 +298,9 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
         stamp(ev ? &ev->trace : nullptr, true);
         if (counters)
             k_trace<true><<<trace_blocks, 128, 0, st>>>(sc->d, P, act[w & 1], counts + w, fetch + w,
-                                                        sc->counters.as<TraceCounters>(), Q);
+                                                        sc->counters.as<TraceCounters>(), Q, tune);
         else
-            k_trace<false><<<trace_blocks, 128, 0, st>>>(sc->d, P, act[w & 1], counts + w, fetch + w, nullptr, Q);
+            k_trace<false><<<trace_blocks, 128, 0, st>>>(sc->d, P, act[w & 1], counts + w, fetch + w, nullptr, Q, tune);
         stamp(ev ? &ev->trace : nullptr, false);
         stamp(ev ? &ev->shade : nullptr, true);
         uint32_t* next_active = act[(w + 1) & 1];
