@@ -152,7 +152,6 @@ GEO_DTYPE = _np.dtype([("pos", "<f4", 3), ("pos_err", "<f4"), ("nor", "<f4", 3),
 
 HOST_LIB = os.path.join(HERE, "libpsy_host.so")
 CUDA_LIB = os.environ.get("PSY_CUDA_LIB", os.path.join(HERE, "libpsy_cuda.so"))  # override: kernel experiments
-ORACLE_LIB = os.path.join(REPO, "oracle", "liboracle.so")
 
 # Every symbol include/psy_cuda.h declares.
 CUDA_SYMBOLS = [

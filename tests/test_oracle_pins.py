@@ -1,0 +1,249 @@
+"""Pins the CPU oracle against every known-answer test the reference's own unit tests hold for the hot
+path and against the self-derived vectors of SURVEY.md 10.  CPU only.
+
+Reference tests restated here (file:line in /root/reference):
+  sub_crates/math3d/src/transform.rs:153-177   multiply_test, inverse_test
+  sub_crates/math3d/src/point.rs:166-201       mul_matrix_1, mul_matrix_3
+  sub_crates/math3d/src/vector.rs:220-236      mul_matrix_1
+  sub_crates/math3d/src/normal.rs:209-220      mul_matrix_1 (<= 4 ulp)
+  src/lerp.rs:140-322                          lerp1-3, lerp_slice1-6, lerp_matrix, lerp_point
+  src/fp_utils.rs:84-131                       inc/dec ulp tests
+  src/hilbert.rs:65-77                         reversible
+"""
+import ctypes as C
+import hashlib
+
+import numpy as np
+
+import oracle_lib as O
+from psychopath_b200 import abi
+
+
+def xf(vals):
+    """Transform::new_from_values(a..l): rows (a b c d / e f g h / i j k l)."""
+    m = abi.PsyXform()
+    for i in range(3):
+        for j in range(4):
+            m.r[i][j] = vals[4 * i + j]
+    return m
+
+
+def xf_vals(m):
+    return [m.r[i][j] for i in range(3) for j in range(4)]
+
+
+A = [1.0, 2.0, 2.0, 1.5, 3.0, 6.0, 7.0, 8.0, 9.0, 2.0, 11.0, 12.0]
+
+
+def test_transform_multiply_exact():
+    lib = O.load()
+    b = [1.0, 5.0, 9.0, 13.0, 2.0, 6.0, 10.0, 14.0, 3.0, 7.0, 11.0, 15.0]
+    c = [97.0, 50.0, 136.0, 162.5, 110.0, 60.0, 156.0, 185.0, 123.0, 70.0, 176.0, 207.5]
+    out = abi.PsyXform()
+    lib.oracle_xform_mul(C.byref(xf(A)), C.byref(xf(b)), C.byref(out))
+    assert xf_vals(out) == c
+
+
+def test_transform_inverse():
+    lib = O.load()
+    a = xf([1.0, 0.33, 0.0, -2.0, 0.0, 1.0, 0.0, 0.0, 2.1, 0.7, 1.3, 0.0])
+    inv = abi.PsyXform()
+    lib.oracle_xform_inverse(C.byref(a), C.byref(inv))
+    prod = abi.PsyXform()
+    lib.oracle_xform_mul(C.byref(a), C.byref(inv), C.byref(prod))
+    ident = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0]
+    assert np.allclose(xf_vals(prod), ident, atol=1e-7)
+
+
+def _apply(fn, m, v):
+    out = (C.c_float * 3)()
+    fn(C.byref(m), (C.c_float * 3)(*v), out)
+    return list(out)
+
+
+def test_point_vector_normal_times_matrix():
+    lib = O.load()
+    assert _apply(lib.oracle_xform_point, xf(A), (1.0, 2.5, 4.0)) == [15.5, 54.0, 70.0]
+    assert _apply(lib.oracle_xform_vector, xf(A), (1.0, 2.5, 4.0)) == [14.0, 46.0, 58.0]
+    n = np.array(_apply(lib.oracle_xform_normal, xf(A), (1.0, 2.5, 4.0)), dtype=np.float32)
+    want = np.array([-4.0625, 1.78125, -0.03125], dtype=np.float32)
+    ulps = np.abs(n.view(np.int32) - want.view(np.int32))
+    assert ulps.max() <= 4
+
+
+def test_point_matrix_composition():
+    lib = O.load()
+    m1, m2 = xf(A), xf([4.0, 1.0, 2.0, 3.5, 3.0, 6.0, 5.0, 2.0, 2.0, 2.0, 4.0, 12.0])
+    m12 = abi.PsyXform()
+    lib.oracle_xform_mul(C.byref(m1), C.byref(m2), C.byref(m12))
+    p = (1.0, 2.5, 4.0)
+    a = np.array(_apply(lib.oracle_xform_point, m12, p))
+    b = np.array(_apply(lib.oracle_xform_point, m2, _apply(lib.oracle_xform_point, m1, p)))
+    assert ((a - b) ** 2).sum() <= 0.00001
+
+
+def test_lerp_matrix_exact_quarters():
+    lib = O.load()
+    a = [0.0, 2.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0, 9.0, 10.0, 11.0]
+    b = [-1.0, 1.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0, 9.0, 10.0, 11.0, 12.0]
+    want = {0.0: a, 1.0: b,
+            0.25: [-0.25, 1.75, 2.25, 3.25, 4.25, 5.25, 6.25, 7.25, 8.25, 9.25, 10.25, 11.25],
+            0.5: [-0.5, 1.5, 2.5, 3.5, 4.5, 5.5, 6.5, 7.5, 8.5, 9.5, 10.5, 11.5],
+            0.75: [-0.75, 1.25, 2.75, 3.75, 4.75, 5.75, 6.75, 7.75, 8.75, 9.75, 10.75, 11.75]}
+    for alpha, w in want.items():
+        out = abi.PsyXform()
+        lib.oracle_xform_lerp(C.byref(xf(a)), C.byref(xf(b)), alpha, C.byref(out))
+        assert xf_vals(out) == w
+
+
+def test_lerp_slice_known_answers():
+    lib = O.load()
+    s = (C.c_float * 5)(0.0, 1.0, 2.0, 3.0, 4.0)
+    for alpha, want in ((0.0, 0.0), (1.0, 4.0), (0.5, 2.0), (0.25, 1.0), (0.75, 3.0), (0.625, 2.5)):
+        assert lib.oracle_lerp_slice_f32(s, 5, alpha) == want
+    two = (C.c_float * 2)(1.0, 2.0)
+    assert lib.oracle_lerp_slice_f32(two, 2, 0.0) == 1.0
+    assert lib.oracle_lerp_slice_f32(two, 2, 1.0) == 2.0
+    assert lib.oracle_lerp_slice_f32(two, 2, 0.5) == 1.5
+
+
+def test_ulp_helpers():
+    lib = O.load()
+    inc, dec = lib.oracle_increment_ulp, lib.oracle_decrement_ulp
+    assert inc(1.0) > 1.0 and inc(-1.0) > -1.0
+    assert dec(1.0) < 1.0 and dec(-1.0) < -1.0
+    assert inc(0.0) > 0.0 and inc(-0.0) > 0.0
+    assert dec(0.0) < 0.0 and dec(-0.0) < 0.0
+    for v in (1.0, -1.0, 1.2, -1.2):
+        v32 = float(np.float32(v))
+        assert dec(inc(v32)) == v32
+        assert inc(dec(v32)) == v32
+
+
+def test_hilbert_known_and_reversible():
+    lib = O.load()
+    want = [(0, 0), (1, 0), (1, 1), (0, 1), (0, 2), (0, 3), (1, 3), (1, 2), (2, 2), (2, 3), (3, 3), (3, 2), (3, 1),
+            (2, 1), (2, 0), (3, 0)]
+    x, y = C.c_uint32(), C.c_uint32()
+    got = []
+    for d in range(16):
+        lib.oracle_hilbert_d2xy(d, C.byref(x), C.byref(y))
+        got.append((x.value, y.value))
+    assert got == want
+    # reversible (hilbert.rs:65-77): d2xy is a bijection on a 64x64 block
+    seen = set()
+    for d in range(64 * 64):
+        lib.oracle_hilbert_d2xy(d, C.byref(x), C.byref(y))
+        assert x.value < 64 and y.value < 64
+        seen.add((x.value, y.value))
+    assert len(seen) == 64 * 64
+
+
+def test_hash_and_golden_ratio_vectors():
+    lib = O.load()
+    assert lib.oracle_hash_u32(0, 0) == 0x00000000
+    assert lib.oracle_hash_u32(1, 0) == 0xE7DE5BAE
+    assert lib.oracle_hash_u32(0x12345678, 1) == 0xD624D67C
+    h = lib.oracle_hash_u32((5 << 16) ^ 7, 1)
+    assert h == 0xC5383481
+    assert np.float32(lib.oracle_golden_ratio_sample(0, h)) == np.float32(0.07516894)
+    assert np.float32(lib.oracle_golden_ratio_sample(3, h)) == np.float32(0.9292709)
+
+
+def test_traversal_table_sha256():
+    lib = O.load()
+    buf = (C.c_uint8 * 384)()
+    lib.oracle_traversal_table(buf)
+    t = bytes(buf)
+    assert hashlib.sha256(t).hexdigest() == "cdb2d257f878635ce8d1ddbbd46bb2f4594db6459d2857a7d30bbe692fe04a5d"
+    assert list(t[0:27]) == [228] * 27 and list(t[27:45]) == [36] * 18 and list(t[45:48]) == [4] * 3
+    assert list(t[48:52]) == [27, 177, 177, 75]
+    assert list(t[7 * 48:7 * 48 + 27]) == [27] * 27
+
+
+def test_fp_gamma_bits():
+    lib = O.load()
+    for n, bits in ((2, 0x34000001), (3, 0x34400002), (5, 0x34A00003), (7, 0x34E00006)):
+        assert np.float32(lib.oracle_fp_gamma(n)).view(np.uint32) == bits
+
+
+def test_probit_vectors():
+    lib = O.load()
+    w = float(np.float32(1.0) / np.float32(3.0))
+    assert lib.oracle_probit(0.5, w) == 0.0
+    for n, want in ((0.25, -0.22482991), (0.75, 0.22482991), (0.01, -0.77544928), (0.99, 0.77544945)):
+        got = np.float32(lib.oracle_probit(n, w))
+        assert abs(int(got.view(np.int32)) - int(np.float32(want).view(np.int32))) <= 1, (n, got)
+
+
+def test_sampler_is_a_stratified_sequence():
+    """sobol_burley is not vendored (parity with upstream unpinned): check the structural properties the
+    restatement must have — values in [0,1), determinism, and (0,2)-net stratification of each Owen-
+    scrambled Sobol dimension over the first 2^k samples."""
+    lib = O.load()
+    out = (C.c_float * 4)()
+    pts = np.zeros((256, 8), dtype=np.float32)
+    for i in range(256):
+        for ds in range(2):
+            lib.oracle_get_sample_4d(i, ds, 17, 33, 12345, out)
+            pts[i, 4 * ds:4 * ds + 4] = list(out)
+    assert (pts >= 0).all() and (pts < 1).all()
+    for k in (4, 6, 8):
+        n = 1 << k
+        for d in range(8):
+            cells = np.floor(pts[:n, d] * n).astype(int)
+            assert len(set(cells.tolist())) == n, (k, d)
+    lib.oracle_get_sample_4d(5, 0, 17, 33, 12345, out)
+    assert list(out) == [float(v) for v in pts[5, :4]]
+    lib.oracle_get_sample_4d(5, 0, 18, 33, 12345, out)
+    assert list(out) != [float(v) for v in pts[5, :4]]
+    # dimension sets >= 2 fall back to the hash (renderer.rs:714-723)
+    lib.oracle_get_sample_4d(5, 3, 17, 33, 12345, out)
+    assert all(0.0 <= v <= 1.0 for v in out)
+
+
+def test_triangle_known_answers():
+    """Woop test on hand-checkable cases (the reference has no triangle tests: analytic pins)."""
+    lib = O.load()
+    f3 = lambda *v: (C.c_float * len(v))(*v)
+    out = (C.c_float * 4)()
+    tri = f3(0, 0, 5, 1, 0, 5, 0, 1, 5)
+    assert lib.oracle_tri_intersect(f3(0.25, 0.25, 0), f3(0, 0, 1), float("inf"), tri, out) == 1
+    assert out[0] == 5.0 and abs(out[1] - 0.5) < 1e-7 and abs(out[2] - 0.25) < 1e-7 and abs(out[3] - 0.25) < 1e-7
+    # beyond max_t, behind the origin, outside the triangle, parallel
+    assert lib.oracle_tri_intersect(f3(0.25, 0.25, 0), f3(0, 0, 1), 4.0, tri, out) == 0
+    assert lib.oracle_tri_intersect(f3(0.25, 0.25, 6), f3(0, 0, 1), float("inf"), tri, out) == 0
+    assert lib.oracle_tri_intersect(f3(0.9, 0.9, 0), f3(0, 0, 1), float("inf"), tri, out) == 0
+    assert lib.oracle_tri_intersect(f3(0.25, 0.25, 0), f3(1, 0, 0), float("inf"), tri, out) == 0
+    # watertight: a ray through the shared edge of two triangles hits at least one of them
+    t1 = f3(0, 0, 5, 1, 0, 5, 0, 1, 5)
+    t2 = f3(1, 0, 5, 1, 1, 5, 0, 1, 5)
+    hits = 0
+    for s in np.linspace(0.0, 1.0, 257):
+        o = f3(float(1 - s), float(s), 0)
+        hits += (lib.oracle_tri_intersect(o, f3(0, 0, 1), float("inf"), t1, out) |
+                 lib.oracle_tri_intersect(o, f3(0, 0, 1), float("inf"), t2, out))
+    assert hits == 257
+
+
+def test_spectral_roundtrip_and_white_furnace():
+    """Meng upsampling: XYZ -> 4 hero wavelengths -> XYZ integrates back to roughly the input colour, and an
+    equal-energy white of luminance 1 upsamples to a flat spectrum of 1 (EQUAL_ENERGY_REFLECTANCE)."""
+    lib = O.load()
+    col = abi.PsyColor(0, 1.0, 1.0, 1.0)
+    e = (C.c_float * 4)()
+    for hero in (380.0, 455.5, 612.25, 700.0):
+        lib.oracle_color_to_spectral(C.byref(col), hero, e)
+        assert np.allclose(list(e), 1.0, atol=2e-3), list(e)
+    # Monte-Carlo round trip of a saturated-ish colour
+    col = abi.PsyColor(0, 0.35, 0.45, 0.2)
+    acc = np.zeros(3)
+    n = 4096
+    xyz = (C.c_float * 3)()
+    for i in range(n):
+        hero = 380.0 + 320.0 * ((i + 0.5) / n)
+        lib.oracle_color_to_spectral(C.byref(col), hero, e)
+        lib.oracle_xyz_from_spectral(e, hero, xyz)
+        acc += np.array(list(xyz))
+    acc /= n
+    assert np.allclose(acc, [0.35, 0.45, 0.2], rtol=0.08, atol=0.01), acc
