@@ -14,6 +14,15 @@ struct DPath {
     uint32_t xf_count;    // 0 = no transform anywhere on the chain (space.is_empty())
 };
 
+// Flattened per-path record read on instance entry by the trace kernel (2 x uint4):
+//   r0 = { kind | own_xform << 3 | xf_count << 8, xf_base, child_base, instance id }
+//   r1 = mesh:     { BVH root ref, tri_base, tv_base, n_keys }
+//        assembly: { BVH root ref, instance_base, assembly index, 0 }
+//        light:    { light index, 0, 0, 0 }
+// plus, at path_static[6*p .. 6*p+6], the single composed world->local key (3 rows) and its inverse
+// (3 rows) for static paths, so that all loads of an entry have addresses known from `p` alone.
+constexpr uint32_t PATH_MESH = 0, PATH_SPHERE_LIGHT = 1, PATH_RECT_LIGHT = 2, PATH_ASSEMBLY = 3, PATH_EMPTY = 4;
+
 struct DMesh {
     uint32_t root, tri_base, tri_count, n_keys;
     uint32_t tv_base;    // first float4 of this mesh's gathered triangle vertices
@@ -46,7 +55,11 @@ struct DScene {
     const DPath* paths;
     const float4* path_xforms;  // composed keys, 3 rows each
     const float4* path_inv;     // per path: inverse of the single composed key (valid when xf_count == 1)
+    const uint4* path_recs;     // 2 per path, see PATH_* above
+    const float4* path_static;  // 6 per path
     uint32_t root_assembly;
+    uint32_t root_bvh;            // child reference of the root assembly's BVH4
+    uint32_t root_instance_base;  // first instance of the root assembly
     uint32_t n_paths;
     // camera
     const float4* cam_xforms;

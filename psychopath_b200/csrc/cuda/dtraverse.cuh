@@ -4,7 +4,7 @@
 // motion-lerped local->world matrix, the stack of child references), so a warp can stop after a
 // bounded number of steps, retire finished lanes, hand them new rays and continue ("persistent
 // threads with lane refill").  begin() = the per-ray prologue of TracerInner::trace
-// (src/tracer.rs:59-77), run() = BVH4::traverse (src/accel/bvh4.rs:101-184) with the instance
+// (src/tracer.rs:59-77), run_warp() = BVH4::traverse (src/accel/bvh4.rs:101-184) with the instance
 // push/pop of trace_assembly (src/tracer.rs:87-150) and the leaf tests of
 // TriangleMesh::intersect_rays (src/surface/triangle_mesh.rs:174-262) folded into one loop.
 #pragma once
@@ -12,21 +12,18 @@
 
 namespace psyd {
 
+// Words saved per nesting level when the ray enters an instance: the parent's local-space ray, so
+// that leaving the instance is a reload instead of the reference's recomputation
+// (tracer.rs:131-148 calls update_local again; same inputs, same bits).
+constexpr int CTX_WORDS = 10;
+
 struct TraversalMem {
     uint32_t stack[TRACE_STACK_SIZE];
-    uint32_t ctx[3 * TRACE_MAX_NEST];
+    uint32_t ctx[CTX_WORDS * (TRACE_MAX_NEST + 1)];  // the last slot belongs to the mesh level
 };
 
 template <bool COUNT>
 struct Traversal {
-    PSY_DEV void attach(TraversalMem& m) {
-        stack = m.stack;
-        ctx_asm = m.ctx;
-        ctx_base = m.ctx + TRACE_MAX_NEST;
-        ctx_active = m.ctx + 2 * TRACE_MAX_NEST;
-        sp = 0;
-        pend = PSY_NONE;
-    }
     // the ray (world space)
     V3 orig, dir;
     float time;
@@ -37,21 +34,28 @@ struct Traversal {
     V3 orig_local, dir_inv_local;
     bool finite_dir_inv;  // no inf/NaN in the local ray: the slab test cannot produce NaN
     // assembly-level context
-    uint32_t cur_asm, path_base, active_path;
-    // The dynamically indexed arrays live outside the struct (TraversalMem) so that every scalar member
-    // can be promoted to a register.
-    uint32_t *ctx_asm, *ctx_base, *ctx_active;
+    uint32_t path_base;      // first path of the current assembly's instances
+    uint32_t asm_inst_base;  // first instance of the current assembly
     int ctx_n;
     // mesh-level context
-    bool in_mesh, mesh_own_xform, space_empty;
-    uint32_t mesh_parent_active, mesh_path;
+    bool in_mesh, space_empty;
+    uint32_t mesh_path;
     uint32_t mesh_tri_base, mesh_tv_base, mesh_n_keys;
     Xf mat_space;
-    // stack of child references / markers
+    // The dynamically indexed arrays live outside the struct (TraversalMem) so that every scalar member
+    // can be promoted to a register.
     uint32_t* stack;
+    uint32_t* ctx;
     int sp;
     uint32_t pend;  // parked leaf / instance reference, PSY_NONE when none
     HitRec hit;
+
+    PSY_DEV void attach(TraversalMem& m) {
+        stack = m.stack;
+        ctx = m.ctx;
+        sp = 0;
+        pend = PSY_NONE;
+    }
 
     PSY_DEV void set_local(const Xf& x) {
         orig_local = xf_point(x, orig);
@@ -60,9 +64,24 @@ struct Traversal {
         finite_dir_inv = fabsf(dir_inv_local.x) <= big && fabsf(dir_inv_local.y) <= big && fabsf(dir_inv_local.z) <= big &&
                          fabsf(orig_local.x) <= big && fabsf(orig_local.y) <= big && fabsf(orig_local.z) <= big;
     }
-    PSY_DEV void restore_local(const DScene& S) {
-        Xf x = active_path == PSY_NONE ? xf_identity() : path_xform(S, S.paths[active_path], time);
-        set_local(x);
+    PSY_DEV void save_ctx(int level, uint32_t own) {
+        uint32_t* c = ctx + level * CTX_WORDS;
+        c[0] = path_base;
+        c[1] = asm_inst_base;
+        c[2] = own | (finite_dir_inv ? 2u : 0u);
+        c[3] = __float_as_uint(orig_local.x), c[4] = __float_as_uint(orig_local.y), c[5] = __float_as_uint(orig_local.z);
+        c[6] = __float_as_uint(dir_inv_local.x), c[7] = __float_as_uint(dir_inv_local.y);
+        c[8] = __float_as_uint(dir_inv_local.z);
+    }
+    PSY_DEV void load_ctx(int level) {
+        const uint32_t* c = ctx + level * CTX_WORDS;
+        path_base = c[0];
+        asm_inst_base = c[1];
+        if (c[2] & 1u) {  // the instance we are leaving had its own transform: restore the parent's local ray
+            finite_dir_inv = (c[2] & 2u) != 0u;
+            orig_local = mk3(__uint_as_float(c[3]), __uint_as_float(c[4]), __uint_as_float(c[5]));
+            dir_inv_local = mk3(__uint_as_float(c[6]), __uint_as_float(c[7]), __uint_as_float(c[8]));
+        }
     }
 
     PSY_DEV void begin(const DScene& S, const RayIn& ray) {
@@ -75,18 +94,16 @@ struct Traversal {
         hit.pad = 0;
         pre = tri_precompute(dir);
         set_local(xf_identity());  // tracer.rs:66-69: update_local(i, identity), evaluated literally
-        cur_asm = S.root_assembly;
         path_base = 0;
-        active_path = PSY_NONE;
+        asm_inst_base = S.root_instance_base;
         ctx_n = 0;
-        in_mesh = false, mesh_own_xform = false, space_empty = true;
-        mesh_parent_active = PSY_NONE, mesh_path = 0;
+        in_mesh = false, space_empty = true;
+        mesh_path = 0;
         mesh_tri_base = 0, mesh_tv_base = 0, mesh_n_keys = 1;
         mat_space = xf_identity();
         sp = 0;
         pend = PSY_NONE;
-        uint32_t root = S.assemblies[cur_asm].root;
-        if (root != PSY_NONE) stack[sp++] = root;
+        if (S.root_bvh != PSY_NONE) stack[sp++] = S.root_bvh;
     }
 
     PSY_DEV bool done() const { return sp == 0 && pend == PSY_NONE; }
@@ -229,107 +246,109 @@ struct Traversal {
         return false;
     }
 
-    // ---- instance (tracer.rs:94-149); assembly leaves hold exactly one instance
+    // world->local transform of path p at the ray's time, from the flattened path record
+    PSY_DEV Xf rec_xform(const DScene& S, uint32_t p, uint32_t xf_count, uint32_t xf_base) const {
+        if (xf_count == 1u) return xf_load(S.path_static + 6 * (size_t)p);
+        if (xf_count == 0u) return xf_identity();
+        return lerp_slice_xf(S.path_xforms + 3 * (size_t)xf_base, xf_count, time);
+    }
+
+    // ---- instance (tracer.rs:94-149); assembly leaves hold exactly one instance.  Everything the entry
+    // needs comes from one 32-byte path record (+ the static transform pair at an address that depends
+    // only on the path number), i.e. one level of dependent loads.
     PSY_DEV bool visit_instance(const DScene& S, uint32_t start, TraceCounters& cnt) {
-        const PsyInstance inst = S.instances[start];
-        uint32_t p = path_base + (start - S.assemblies[cur_asm].instance_base);
-        const DPath P = S.paths[p];
-        bool own = inst.xform_count > 0;
+        const uint32_t p = path_base + (start - asm_inst_base);
+        const uint4 r0 = __ldg(S.path_recs + 2 * (size_t)p);
+        const uint4 r1 = __ldg(S.path_recs + 2 * (size_t)p + 1);
+        const uint32_t kind = r0.x & 7u;
+        const uint32_t own = (r0.x >> 3) & 1u;
+        const uint32_t xf_count = r0.x >> 8;
         if (COUNT) cnt.instance_visits += 1;
-        if (inst.kind == PSY_INSTANCE_OBJECT) {
-            const PsyObject obj = S.objects[inst.data_index];
-            if (obj.kind == PSY_OBJECT_MESH) {
-                const DMesh mesh = S.meshes[obj.index];
-                if (mesh.root == PSY_NONE) return false;
-                mesh_tri_base = mesh.tri_base, mesh_tv_base = mesh.tv_base, mesh_n_keys = mesh.n_keys;
-                mesh_parent_active = active_path;
-                mesh_own_xform = own;
-                mesh_path = p;
-                active_path = p;
-                space_empty = P.xf_count == 0;
-                if (own) set_local(path_xform(S, P, time));
-                if (!space_empty) mat_space = path_mat_space(S, P, p, time);
-                in_mesh = true;
-                stack[sp++] = MARK_POP_MESH;
-                stack[sp++] = mesh.root;
-            } else {
-                const PsyLight l = S.lights[obj.index];
-                Xf xform = path_xform(S, P, time);
-                if (l.kind == PSY_LIGHT_SPHERE) {
-                    V3 ol = own ? xf_point(xform, orig) : orig_local;
-                    float t;
-                    if (sphere_light_hit(S, l, xform, ol, dir, time, max_t, t)) {
+        if (kind == PATH_MESH) {
+            save_ctx(TRACE_MAX_NEST, own);
+            mesh_tri_base = r1.y, mesh_tv_base = r1.z, mesh_n_keys = r1.w;
+            mesh_path = p;
+            space_empty = xf_count == 0u;
+            if (xf_count == 1u) {
+                if (own) set_local(xf_load(S.path_static + 6 * (size_t)p));
+                mat_space = xf_load(S.path_static + 6 * (size_t)p + 3);
+            } else if (xf_count > 1u) {
+                // transform motion blur: lerp the two keys around the ray's time, invert per ray in
+                // registers (triangle_mesh.rs:183-189)
+                Xf x = lerp_slice_xf(S.path_xforms + 3 * (size_t)r0.y, xf_count, time);
+                if (own) set_local(x);
+                mat_space = xf_inverse(x);
+            }
+            in_mesh = true;
+            stack[sp++] = MARK_POP_MESH;
+            stack[sp++] = r1.x;
+        } else if (kind == PATH_ASSEMBLY) {
+            if (ctx_n >= TRACE_MAX_NEST) return false;
+            save_ctx(ctx_n, own);
+            ++ctx_n;
+            path_base = r0.z;
+            asm_inst_base = r1.y;
+            if (own) set_local(rec_xform(S, p, xf_count, r0.y));
+            stack[sp++] = MARK_POP_ASM;
+            stack[sp++] = r1.x;
+        } else if (kind == PATH_SPHERE_LIGHT) {
+            const PsyLight l = S.lights[r1.x];
+            Xf xform = rec_xform(S, p, xf_count, r0.y);
+            V3 ol = own ? xf_point(xform, orig) : orig_local;
+            float t;
+            if (sphere_light_hit(S, l, xform, ol, dir, time, max_t, t)) {
+                if (occlusion) {
+                    hit.kind = PSY_HIT_OCCLUDED;
+                    return true;
+                }
+                max_t = t;
+                hit.kind = PSY_HIT_SPHERE_LIGHT;
+                hit.t = t;
+                hit.prim = 0;
+                hit.path = p;
+                hit.b0 = hit.b1 = hit.b2 = 0.0f;
+            }
+        } else if (kind == PATH_RECT_LIGHT) {
+            const PsyLight l = S.lights[r1.x];
+            Xf xform = rec_xform(S, p, xf_count, r0.y);
+            float w, h;
+            rect_dims(S, l, time, w, h);
+            Xf space_inv = xf_inverse(xform);
+            V3 p1, p2, p3, p4;
+            rect_corners(space_inv, w, h, p1, p2, p3, p4);
+#pragma unroll 1
+            for (int k = 0; k < 2; ++k) {
+                V3 a = k == 0 ? p1 : p3, b = k == 0 ? p2 : p4, c = k == 0 ? p3 : p1;
+                float t, b0, b1, b2;
+                if (COUNT) cnt.tri_tests += 1;
+                if (tri_intersect(orig, pre, max_t, a, b, c, t, b0, b1, b2)) {
+                    if (t < max_t) {
                         if (occlusion) {
                             hit.kind = PSY_HIT_OCCLUDED;
                             return true;
                         }
                         max_t = t;
-                        hit.kind = PSY_HIT_SPHERE_LIGHT;
+                        hit.kind = PSY_HIT_RECT_LIGHT;
                         hit.t = t;
-                        hit.prim = 0;
+                        hit.prim = (uint32_t)k;
                         hit.path = p;
-                        hit.b0 = hit.b1 = hit.b2 = 0.0f;
-                    }
-                } else {
-                    float w, h;
-                    rect_dims(S, l, time, w, h);
-                    Xf space_inv = xf_inverse(xform);
-                    V3 p1, p2, p3, p4;
-                    rect_corners(space_inv, w, h, p1, p2, p3, p4);
-#pragma unroll 1
-                    for (int k = 0; k < 2; ++k) {
-                        V3 a = k == 0 ? p1 : p3, b = k == 0 ? p2 : p4, c = k == 0 ? p3 : p1;
-                        float t, b0, b1, b2;
-                        if (COUNT) cnt.tri_tests += 1;
-                        if (tri_intersect(orig, pre, max_t, a, b, c, t, b0, b1, b2)) {
-                            if (t < max_t) {
-                                if (occlusion) {
-                                    hit.kind = PSY_HIT_OCCLUDED;
-                                    return true;
-                                }
-                                max_t = t;
-                                hit.kind = PSY_HIT_RECT_LIGHT;
-                                hit.t = t;
-                                hit.prim = (uint32_t)k;
-                                hit.path = p;
-                                hit.b0 = b0, hit.b1 = b1, hit.b2 = b2;
-                                break;
-                            }
-                        }
+                        hit.b0 = b0, hit.b1 = b1, hit.b2 = b2;
+                        break;
                     }
                 }
             }
-        } else {
-            // sub-assembly (tracer.rs:125-127)
-            const PsyAssembly sub = S.assemblies[inst.data_index];
-            if (sub.root == PSY_NONE || ctx_n >= TRACE_MAX_NEST) return false;
-            ctx_asm[ctx_n] = cur_asm;
-            ctx_base[ctx_n] = path_base;
-            ctx_active[ctx_n] = active_path;
-            ++ctx_n;
-            cur_asm = inst.data_index;
-            path_base = P.child_base;
-            active_path = p;
-            if (own) set_local(path_xform(S, P, time));
-            stack[sp++] = MARK_POP_ASM;
-            stack[sp++] = sub.root;
         }
         return false;
     }
 
     // Marker handling (leaving an object instance / a sub-assembly): tracer.rs:131-148
-    PSY_DEV void pop_marker(const DScene& S, uint32_t ref) {
+    PSY_DEV void pop_marker(uint32_t ref) {
         if (ref == MARK_POP_MESH) {
             in_mesh = false;
-            active_path = mesh_parent_active;
-            if (mesh_own_xform) restore_local(S);
+            load_ctx(TRACE_MAX_NEST);
         } else {
             --ctx_n;
-            bool own = S.instances[S.paths[active_path].inst].xform_count > 0;
-            cur_asm = ctx_asm[ctx_n];
-            path_base = ctx_base[ctx_n];
-            active_path = ctx_active[ctx_n];
-            if (own) restore_local(S);
+            load_ctx(ctx_n);
         }
     }
 
@@ -340,9 +359,9 @@ struct Traversal {
     //     `leaf_min` lanes hold a parked entry of that kind, or until no lane has node work left —
     //     then they run the expensive leaf / instance code together.
     // The per-ray order of node visits and primitive tests is exactly that of the plain stack loop, so
-    // results are bit-identical; only the interleaving between lanes changes.  (Three measurements on
-    // B200, C4 scene: per-lane `while(sp>0)` loops 1.9 active threads/instruction, lock-step steps
-    // without parking 6.5-9.2, with parking see profiles/.)
+    // results are bit-identical; only the interleaving between lanes changes.  (Measured on B200, C4
+    // scene: per-lane `while(sp>0)` loops 1.9 active threads/instruction, lock-step steps without
+    // parking 6.5-9.2; see profiles/.)
     // Ends when no lane has work, after `budget` iterations, or when `refill_min` lanes are idle.
     PSY_DEV void run_warp(const DScene& S, int budget, int refill_min, int leaf_min, TraceCounters& cnt) {
         const uint32_t FULL = 0xffffffffu;
@@ -358,7 +377,7 @@ struct Traversal {
                     visit_node(S, ref, cnt);
                     did_node = true;
                 } else if (ref >= MARK_POP_ASM) {
-                    pop_marker(S, ref);
+                    pop_marker(ref);
                     did_node = true;
                 } else {
                     pend = ref;

@@ -73,7 +73,7 @@ struct PsyScene {
     uint64_t upload_bytes = 0;
     DevBuf nodes, motion, tri_verts, tris, normals, meshes, lights, light_shape, light_colors, objects, shaders,
         assemblies, instances, light_instances, light_inst_local, xforms, light_nodes, lt_bounds, paths, path_xforms,
-        path_inv, cam_xforms, cam_tfovs, cam_aperture, cam_focus, distant, world_floats, meng;
+        path_inv, path_recs, path_static, cam_xforms, cam_tfovs, cam_aperture, cam_focus, distant, world_floats, meng;
     // path pool
     size_t pool_cap = 0;
     DevBuf pool_ray_o, pool_ray_d, pool_flags, pool_sseed, pool_wl, pool_cpdf, pool_nb_o, pool_nb_d, pool_next_atten,
@@ -620,6 +620,40 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
             }
         }
     }
+    // flattened path records for the trace kernel's instance entry (dscene.cuh PATH_*)
+    std::vector<uint4> path_recs(paths.size() * 2);
+    std::vector<PsyXform> path_static(paths.size() * 2);
+    for (size_t i = 0; i < paths.size(); ++i) {
+        const PsyInstance& in = s->instances[dpaths[i].inst];
+        uint32_t kind = PATH_EMPTY;
+        uint4 r1 = make_uint4(0, 0, 0, 0);
+        if (in.kind == PSY_INSTANCE_ASSEMBLY) {
+            const PsyAssembly& a = s->assemblies[in.data_index];
+            if (a.root != PSY_NONE) {
+                kind = PATH_ASSEMBLY;
+                r1 = make_uint4(a.root, a.instance_base, in.data_index, 0);
+            }
+        } else {
+            const PsyObject& o = s->objects[in.data_index];
+            if (o.kind == PSY_OBJECT_MESH) {
+                const DMesh& m = dmeshes[o.index];
+                if (m.root != PSY_NONE) {
+                    kind = PATH_MESH;
+                    r1 = make_uint4(m.root, m.tri_base, m.tv_base, m.n_keys);
+                }
+            } else {
+                kind = s->lights[o.index].kind == PSY_LIGHT_SPHERE ? PATH_SPHERE_LIGHT : PATH_RECT_LIGHT;
+                r1 = make_uint4(o.index, 0, 0, 0);
+            }
+        }
+        uint32_t own = in.xform_count > 0 ? 1u : 0u;
+        path_recs[2 * i] = make_uint4(kind | (own << 3) | (dpaths[i].xf_count << 8), dpaths[i].xf_base,
+                                      dpaths[i].child_base, in.id);
+        path_recs[2 * i + 1] = r1;
+        path_static[2 * i] = paths[i].keys.size() == 1 ? psyh::to_abi(paths[i].keys[0]) : psyh::to_abi(HXf());
+        path_static[2 * i + 1] = path_inv[i];
+    }
+
     std::vector<float4> normals4(s->n_vert_keys);
     bool any_normals = false;
     for (uint32_t m = 0; m < s->n_meshes; ++m) any_normals |= s->meshes[m].has_normals != 0;
@@ -674,6 +708,8 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
     UP(paths, dpaths.data(), dpaths.size());
     UP(path_xforms, path_xf.data(), path_xf.size());
     UP(path_inv, path_inv.data(), path_inv.size());
+    UP(path_recs, path_recs.data(), path_recs.size());
+    UP(path_static, path_static.data(), path_static.size());
     UP(cam_xforms, s->camera.xforms, (size_t)s->camera.n_xforms);
     UP(cam_tfovs, s->camera.tfovs, (size_t)s->camera.n_tfovs);
     UP(cam_aperture, s->camera.aperture_radii, (size_t)s->camera.n_aperture_radii);
@@ -710,6 +746,10 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
     d.paths = sc->paths.as<DPath>();
     d.path_xforms = sc->path_xforms.as<float4>();
     d.path_inv = sc->path_inv.as<float4>();
+    d.path_recs = sc->path_recs.as<uint4>();
+    d.path_static = sc->path_static.as<float4>();
+    d.root_bvh = s->assemblies[s->root_assembly].root;
+    d.root_instance_base = s->assemblies[s->root_assembly].instance_base;
     d.root_assembly = s->root_assembly;
     d.n_paths = (uint32_t)dpaths.size();
     d.cam_xforms = sc->cam_xforms.as<float4>();
