@@ -55,17 +55,21 @@ PSY_DEV float max_abs_3(float a, float b, float c) {
     if (b > c) return b;
     return c;
 }
-// triangle::intersect_ray (triangle.rs:58-149)
-PSY_DEV bool tri_intersect(V3 orig, const RayTriPre& pre, float max_t, V3 t0, V3 t1, V3 t2, float& t, float& b0,
-                           float& b1, float& b2) {
-    V3 p0 = t0 - orig, p1 = t1 - orig, p2 = t2 - orig;
-    float p0k = comp(p0, pre.zi), p1k = comp(p1, pre.zi), p2k = comp(p2, pre.zi);
-    float p0x = comp(p0, pre.xi) - (pre.sx * p0k);
-    float p0y = comp(p0, pre.yi) - (pre.sy * p0k);
-    float p1x = comp(p1, pre.xi) - (pre.sx * p1k);
-    float p1y = comp(p1, pre.yi) - (pre.sy * p1k);
-    float p2x = comp(p2, pre.xi) - (pre.sx * p2k);
-    float p2y = comp(p2, pre.yi) - (pre.sy * p2k);
+// Components of v in the ray's permuted axis order (xi, yi, zi)
+PSY_DEV V3 permute3(V3 v, const RayTriPre& pre) { return mk3(comp(v, pre.xi), comp(v, pre.yi), comp(v, pre.zi)); }
+
+// triangle::intersect_ray (triangle.rs:58-149) on inputs that are already in the ray's permuted axis
+// order: q_i = permute(tri_i), orig_p = permute(orig).  Per component the arithmetic is the reference's.
+PSY_DEV bool tri_intersect_perm(V3 orig_p, const RayTriPre& pre, float max_t, V3 q0, V3 q1, V3 q2, float& t, float& b0,
+                                float& b1, float& b2) {
+    V3 p0 = q0 - orig_p, p1 = q1 - orig_p, p2 = q2 - orig_p;
+    float p0k = p0.z, p1k = p1.z, p2k = p2.z;
+    float p0x = p0.x - (pre.sx * p0k);
+    float p0y = p0.y - (pre.sy * p0k);
+    float p1x = p1.x - (pre.sx * p1k);
+    float p1y = p1.y - (pre.sy * p1k);
+    float p2x = p2.x - (pre.sx * p2k);
+    float p2y = p2.y - (pre.sy * p2k);
     float e0 = (p1x * p2y) - (p1y * p2x);
     float e1 = (p2x * p0y) - (p2y * p0x);
     float e2 = (p0x * p1y) - (p0y * p1x);
@@ -102,6 +106,11 @@ PSY_DEV bool tri_intersect(V3 orig, const RayTriPre& pre, float max_t, V3 t0, V3
         if (t <= dt) return false;
     }
     return true;
+}
+PSY_DEV bool tri_intersect(V3 orig, const RayTriPre& pre, float max_t, V3 t0, V3 t1, V3 t2, float& t, float& b0,
+                           float& b1, float& b2) {
+    return tri_intersect_perm(permute3(orig, pre), pre, max_t, permute3(t0, pre), permute3(t1, pre), permute3(t2, pre), t,
+                              b0, b1, b2);
 }
 
 PSY_DEV V3 f4_xyz(float4 v) { return mk3(v.x, v.y, v.z); }

@@ -30,9 +30,11 @@ struct Traversal {
     float max_t;
     bool occlusion;
     RayTriPre pre;
+    V3 orig_p;  // origin in the ray's permuted axis order (Woop test)
     // current space
     V3 orig_local, dir_inv_local;
     bool finite_dir_inv;  // no inf/NaN in the local ray: the slab test cannot produce NaN
+    uint32_t octant;      // ray_code(dir_inv_local): row of TRAVERSAL_TABLE (bvh4.rs:29-34,111-112)
     // assembly-level context
     uint32_t path_base;      // first path of the current assembly's instances
     uint32_t asm_inst_base;  // first instance of the current assembly
@@ -41,7 +43,8 @@ struct Traversal {
     bool in_mesh, space_empty;
     uint32_t mesh_path;
     uint32_t mesh_tri_base, mesh_tv_base, mesh_n_keys;
-    Xf mat_space;
+    Xf mat_space;  // local->world of the current mesh instance, output components already in the ray's
+                   // permuted axis order so the transformed vertices feed the Woop test without selects
     // The dynamically indexed arrays live outside the struct (TraversalMem) so that every scalar member
     // can be promoted to a register.
     uint32_t* stack;
@@ -57,12 +60,18 @@ struct Traversal {
         pend = PSY_NONE;
     }
 
+    PSY_DEV Xf xf_permuted(const Xf& m) const {
+        Xf r;
+        r.X = permute3(m.X, pre), r.Y = permute3(m.Y, pre), r.Z = permute3(m.Z, pre), r.T = permute3(m.T, pre);
+        return r;
+    }
     PSY_DEV void set_local(const Xf& x) {
         orig_local = xf_point(x, orig);
         dir_inv_local = recip3(xf_vector(x, dir));
         const float big = 3.402823466e+38f;
         finite_dir_inv = fabsf(dir_inv_local.x) <= big && fabsf(dir_inv_local.y) <= big && fabsf(dir_inv_local.z) <= big &&
                          fabsf(orig_local.x) <= big && fabsf(orig_local.y) <= big && fabsf(orig_local.z) <= big;
+        octant = (uint32_t)ray_code(dir_inv_local);
     }
     PSY_DEV void save_ctx(int level, uint32_t own) {
         uint32_t* c = ctx + level * CTX_WORDS;
@@ -81,6 +90,7 @@ struct Traversal {
             finite_dir_inv = (c[2] & 2u) != 0u;
             orig_local = mk3(__uint_as_float(c[3]), __uint_as_float(c[4]), __uint_as_float(c[5]));
             dir_inv_local = mk3(__uint_as_float(c[6]), __uint_as_float(c[7]), __uint_as_float(c[8]));
+            octant = (uint32_t)ray_code(dir_inv_local);
         }
     }
 
@@ -93,6 +103,7 @@ struct Traversal {
         hit.b0 = hit.b1 = hit.b2 = 0.0f;
         hit.pad = 0;
         pre = tri_precompute(dir);
+        orig_p = permute3(orig, pre);
         set_local(xf_identity());  // tracer.rs:66-69: update_local(i, identity), evaluated literally
         path_base = 0;
         asm_inst_base = S.root_instance_base;
@@ -206,14 +217,16 @@ struct Traversal {
         }
 #undef PSY_SLAB
         if (hits) {
-            uint32_t order_code = c_traversal_table[ray_code(dir_inv_local)][meta.x];
-            for (int i = (int)meta.w; i > 0;) {
-                --i;
-                uint32_t child_i = (order_code >> (i * 2)) & 3u;
-                if (hits & (1u << child_i)) {
-                    uint32_t c = child_i == 0 ? child.x : (child_i == 1 ? child.y : (child_i == 2 ? child.z : child.w));
-                    stack[sp++] = c;
-                }
+            // push far -> near: order position i = n-1 .. 0, so position 0 is popped first (bvh4.rs:152-165).
+            // Fully unrolled and predicated: every lane runs the same four slots.
+            const uint32_t order_code = c_traversal_table[octant][meta.x];
+#pragma unroll
+            for (int i = 3; i >= 0; --i) {
+                const uint32_t child_i = (order_code >> (i * 2)) & 3u;
+                const uint32_t lo = (child_i & 1u) ? child.y : child.x;
+                const uint32_t hi = (child_i & 1u) ? child.w : child.z;
+                const uint32_t c = (child_i & 2u) ? hi : lo;
+                if ((uint32_t)i < meta.w && ((hits >> child_i) & 1u)) stack[sp++] = c;
             }
         }
     }
@@ -227,10 +240,12 @@ struct Traversal {
                 p0 = xf_point(mat_space, p0);
                 p1 = xf_point(mat_space, p1);
                 p2 = xf_point(mat_space, p2);
+            } else {
+                p0 = permute3(p0, pre), p1 = permute3(p1, pre), p2 = permute3(p2, pre);
             }
             if (COUNT) cnt.tri_tests += 1;
             float t, b0, b1, b2;
-            if (tri_intersect(orig, pre, max_t, p0, p1, p2, t, b0, b1, b2)) {
+            if (tri_intersect_perm(orig_p, pre, max_t, p0, p1, p2, t, b0, b1, b2)) {
                 if (occlusion) {
                     hit.kind = PSY_HIT_OCCLUDED;
                     return true;
@@ -271,13 +286,13 @@ struct Traversal {
             space_empty = xf_count == 0u;
             if (xf_count == 1u) {
                 if (own) set_local(xf_load(S.path_static + 6 * (size_t)p));
-                mat_space = xf_load(S.path_static + 6 * (size_t)p + 3);
+                mat_space = xf_permuted(xf_load(S.path_static + 6 * (size_t)p + 3));
             } else if (xf_count > 1u) {
                 // transform motion blur: lerp the two keys around the ray's time, invert per ray in
                 // registers (triangle_mesh.rs:183-189)
                 Xf x = lerp_slice_xf(S.path_xforms + 3 * (size_t)r0.y, xf_count, time);
                 if (own) set_local(x);
-                mat_space = xf_inverse(x);
+                mat_space = xf_permuted(xf_inverse(x));
             }
             in_mesh = true;
             stack[sp++] = MARK_POP_MESH;
