@@ -498,26 +498,41 @@ PSY_DEV void flip_normals(V3 inc, V3 nor, V3 nor_g, V3& nn, V3& fng) {
 // specialised per closure class), or CLOSURE_ANY to branch on cl.kind.
 constexpr uint32_t CLOSURE_ANY = 0xFFu;
 #define PSY_KIND_IS(K) ((KIND == CLOSURE_ANY) ? (cl.kind == (K)) : (KIND == (K)))
+
+// What sample() and evaluate() of one hit share: the closure colour at the path's hero wavelengths and
+// the flipped normals.  The reference recomputes them in every call (surface_closure.rs:284-332,
+// 420-533); they depend only on (closure, inc, nor, nor_g, wavelength), so one evaluation per hit gives
+// the same bits.
+struct ShadeCtx {
+    V4 spec;     // color.to_spectral_sample(wavelength).e
+    V3 nn, fng;  // flipped normalised shading normal / flipped geometric normal
+    V3 aa;       // ggx: -inc.normalized()
+};
 template <uint32_t KIND>
-__device__ __noinline__ void closure_evaluate(const DScene& S, const Closure& cl, V3 inc, V3 out, V3 nor, V3 nor_g,
-                                              float wl, V4& filter, float& pdf) {
+PSY_DEV ShadeCtx closure_prepare(const DScene& S, const Closure& cl, V3 inc, V3 nor, V3 nor_g, float wl) {
+    ShadeCtx c;
+    c.spec = color_to_spectral(S, cl.color, wl);
+    flip_normals(inc, nor, nor_g, c.nn, c.fng);
+    c.aa = mk3(0, 0, 0);
+    if (PSY_KIND_IS(PSY_SHADER_GGX)) c.aa = -normalized(inc);
+    return c;
+}
+template <uint32_t KIND>
+PSY_DEV void closure_evaluate(const Closure& cl, const ShadeCtx& sc, V3 out, V4& filter, float& pdf) {
     if (PSY_KIND_IS(PSY_SHADER_LAMBERT)) {
-        V3 nn, fng;
-        flip_normals(inc, nor, nor_g, nn, fng);
-        if (dot(fng, out) >= 0.0f) {
-            float fac = rmax(dot(nn, normalized(out)), 0.0f) * PSY_INV_PI;
-            filter = color_to_spectral(S, cl.color, wl) * fac;
+        if (dot(sc.fng, out) >= 0.0f) {
+            float fac = rmax(dot(sc.nn, normalized(out)), 0.0f) * PSY_INV_PI;
+            filter = sc.spec * fac;
             pdf = fac;
         } else {
             filter = splat4(0.0f);
             pdf = 0.0f;
         }
     } else if (PSY_KIND_IS(PSY_SHADER_GGX)) {
-        V3 aa = -normalized(inc);
+        V3 aa = sc.aa;
         V3 bb = normalized(out);
         V3 hh = normalized(aa + bb);
-        V3 nn, fng;
-        flip_normals(inc, nor, nor_g, nn, fng);
+        V3 nn = sc.nn, fng = sc.fng;
         if (dot(nn, aa) < 0.0f || dot(nn, bb) < 0.0f || dot(fng, bb) < 0.0f) {
             filter = splat4(0.0f);
             pdf = 0.0f;
@@ -528,7 +543,7 @@ __device__ __noinline__ void closure_evaluate(const DScene& S, const Closure& cl
         float ha = rclamp(dot(hh, aa), -1.0f, 1.0f);
         float hb = rclamp(dot(hh, bb), -1.0f, 1.0f);
         float nh = rclamp(dot(nn, hh), -1.0f, 1.0f);
-        V4 ss = color_to_spectral(S, cl.color, wl);
+        V4 ss = sc.spec;
         float rev_fresnel = 1.0f - cl.fresnel;
         V4 col_f;
 #pragma unroll
@@ -544,46 +559,42 @@ __device__ __noinline__ void closure_evaluate(const DScene& S, const Closure& cl
         filter = col_f * (dist * g1 * g2) * PSY_INV_PI;
         pdf = dist * PSY_INV_PI;
     } else {
-        filter = color_to_spectral(S, cl.color, wl);
+        filter = sc.spec;
         pdf = 1.0f;
     }
 }
 template <uint32_t KIND>
-PSY_DEV void closure_sample(const DScene& S, const Closure& cl, V3 inc, V3 nor, V3 nor_g, float u, float v, float wl,
-                            V3& dir, V4& filter, float& pdf) {
+PSY_DEV void closure_sample(const Closure& cl, const ShadeCtx& sc, V3 inc, float u, float v, V3& dir, V4& filter,
+                            float& pdf) {
     if (PSY_KIND_IS(PSY_SHADER_LAMBERT)) {
-        V3 nn, fng;
-        flip_normals(inc, nor, nor_g, nn, fng);
         V3 d = cosine_sample_hemisphere(u, v);
         float p = d.z * PSY_INV_PI;
-        V3 out = zup_to_vec(d, nn);
+        V3 out = zup_to_vec(d, sc.nn);
         dir = out;
-        if (dot(fng, out) >= 0.0f) {
-            filter = color_to_spectral(S, cl.color, wl) * p;
+        if (dot(sc.fng, out) >= 0.0f) {
+            filter = sc.spec * p;
             pdf = p;
         } else {
             filter = splat4(0.0f);
             pdf = 0.0f;
         }
     } else if (PSY_KIND_IS(PSY_SHADER_GGX)) {
-        V3 nn, fng;
-        flip_normals(inc, nor, nor_g, nn, fng);
         float theta_cos = half_theta_sample(u, cl.roughness);
         float theta_sin = sqrtf(1.0f - (theta_cos * theta_cos));
         float angle = v * PSY_PI_32 * 2.0f;
         V3 half_dir = mk3(cosf(angle) * theta_sin, sinf(angle) * theta_sin, theta_cos);
-        half_dir = normalized(zup_to_vec(half_dir, nn));
+        half_dir = normalized(zup_to_vec(half_dir, sc.nn));
         V3 out = inc - (half_dir * 2.0f * dot(inc, half_dir));
         dir = out;
-        if (dot(fng, out) >= 0.0f) {
-            closure_evaluate<KIND>(S, cl, inc, out, nor, nor_g, wl, filter, pdf);
+        if (dot(sc.fng, out) >= 0.0f) {
+            closure_evaluate<KIND>(cl, sc, out, filter, pdf);
         } else {
             filter = splat4(0.0f);
             pdf = 0.0f;
         }
     } else {
         dir = mk3(0, 0, 0);
-        filter = color_to_spectral(S, cl.color, wl);
+        filter = sc.spec;
         pdf = 1.0f;
     }
 }
@@ -603,24 +614,42 @@ PSY_DEV float sphere_lambert(float nlcos, float rcos) {
     if (nl < (PSY_H_PI + r)) return (g + h) * PSY_INV_PI;
     return 0.0f;
 }
+// The part of estimate_eval_over_sphere_light that does not depend on the light: evaluated once per
+// light-tree walk instead of once per child (same inputs, same bits).
+struct EstimateCtx {
+    V3 nn;  // flipped, normalised shading normal (lambert: surface_closure.rs:382-389, ggx: :561-567)
+    V3 aa;  // ggx: -inc.normalized()
+};
 template <uint32_t KIND>
-PSY_DEV float closure_estimate_sphere(const Closure& cl, V3 inc, V3 to_light_center, float light_radius_squared, V3 nor,
-                                      V3 nor_g) {
+PSY_DEV EstimateCtx closure_estimate_ctx(const Closure& cl, V3 inc, V3 nor, V3 nor_g) {
+    EstimateCtx e;
+    e.nn = mk3(0, 0, 0), e.aa = mk3(0, 0, 0);
+    if (PSY_KIND_IS(PSY_SHADER_LAMBERT)) {
+        e.nn = dot(nor_g, inc) <= 0.0f ? normalized(nor) : -normalized(nor);
+    } else if (PSY_KIND_IS(PSY_SHADER_GGX)) {
+        e.nn = dot(nor, inc) < 0.0f ? normalized(nor) : -normalized(nor);
+        e.aa = -normalized(inc);
+    }
+    return e;
+}
+template <uint32_t KIND>
+PSY_DEV float closure_estimate_sphere(const Closure& cl, const EstimateCtx& ec, V3 to_light_center,
+                                      float light_radius_squared) {
     if (PSY_KIND_IS(PSY_SHADER_LAMBERT)) {
         float dist2 = length2(to_light_center);
         if (dist2 <= light_radius_squared) return rmin(light_radius_squared / dist2, 4.0f);
         float sin_theta_max2 = rmin(light_radius_squared / dist2, 1.0f);
         float cos_theta_max = sqrtf(1.0f - sin_theta_max2);
         V3 v = normalized(to_light_center);
-        V3 nn = dot(nor_g, inc) <= 0.0f ? normalized(nor) : -normalized(nor);
+        V3 nn = ec.nn;
         float cos_nv = rmin(rmax(dot(nn, v), -1.0f), 1.0f);
         return sphere_lambert(cos_nv, cos_theta_max);
     } else if (PSY_KIND_IS(PSY_SHADER_GGX)) {
         float dist2 = length2(to_light_center);
         float sin_theta_max2 = rmin(light_radius_squared / dist2, 1.0f);
         float cos_theta_max = sqrtf(1.0f - sin_theta_max2);
-        V3 nn = dot(nor, inc) < 0.0f ? normalized(nor) : -normalized(nor);
-        V3 aa = -normalized(inc);
+        V3 nn = ec.nn;
+        V3 aa = ec.aa;
         V3 bb = normalized(to_light_center);
         float theta = acosf(cos_theta_max);
         V3 hh = normalized(aa + bb);
@@ -796,6 +825,7 @@ PSY_DEV bool light_tree_select(const DScene& S, const PsyAssembly& a, V3 inc, V3
     if (a.light_root == PSY_NONE) return false;
     PsyLightNode node = S.light_nodes[a.light_root];
     float tot_prob = 1.0f;
+    const EstimateCtx ec = closure_estimate_ctx<KIND>(sc, inc, nor, nor_g);
     while (node.child_count > 0) {
         float ps[8];
         float total = 0.0f;
@@ -819,7 +849,7 @@ PSY_DEV bool light_tree_select(const DScene& S, const PsyAssembly& a, V3 inc, V3
                 V3 dd = center - pos;
                 float r2 = length2(bmax - bmin) * 0.25f;
                 float inv_surface_area = 1.0f / r2;
-                float approx_contrib = closure_estimate_sphere<KIND>(sc, inc, dd, r2, nor, nor_g);
+                float approx_contrib = closure_estimate_sphere<KIND>(sc, ec, dd, r2);
                 p = nd.energy * inv_surface_area * approx_contrib;
                 total += p;
             }

@@ -321,6 +321,7 @@ PSY_DEV bool path_next(const DScene& S, const PathPool& P, uint32_t slot, const 
     }
     constexpr uint32_t KIND = CLS == SHADE_LAMBERT ? (uint32_t)PSY_SHADER_LAMBERT : (uint32_t)PSY_SHADER_GGX;
     light_attenuation = light_attenuation / closure_sample_pdf;
+    const ShadeCtx shade_ctx = closure_prepare<KIND>(S, is.closure, dir, is.nor, is.nor_g, wl);
 
     // light sample (renderer.rs:488-596)
     uint32_t sseed = P.sseed[slot];
@@ -339,7 +340,7 @@ PSY_DEV bool path_next(const DScene& S, const PathPool& P, uint32_t slot, const 
         float smax;
         V3 ng = normalized(is.nor_g);
         V3 ldir = li.kind == 1 ? li.direction : li.pos - is.pos;
-        closure_evaluate<KIND>(S, is.closure, dir, ldir, is.nor, is.nor_g, wl, attenuation, closure_pdf);
+        closure_evaluate<KIND>(is.closure, shade_ctx, ldir, attenuation, closure_pdf);
         so = robust_ray_origin(is.pos, is.pos_err, ng, ldir);
         if (li.kind == 1) {
             sd = li.direction;
@@ -372,7 +373,7 @@ PSY_DEV bool path_next(const DScene& S, const PathPool& P, uint32_t slot, const 
         V3 bdir;
         V4 filter;
         float pdf;
-        closure_sample<KIND>(S, is.closure, is.incoming, is.nor, is.nor_g, b4[0], b4[1], wl, bdir, filter, pdf);
+        closure_sample<KIND>(is.closure, shade_ctx, is.incoming, b4[0], b4[1], bdir, filter, pdf);
         if ((pdf > 0.0f) && (max_element4(filter) > 0.0f)) {
             next_atten = filter;
             closure_sample_pdf = pdf;
