@@ -7,6 +7,9 @@
 #include <cuda_runtime.h>
 
 #define PSY_DEV __device__ __forceinline__
+// Large, rarely-hot routines (double-precision trig, spectral lookups): one copy per kernel keeps the
+// shade kernels' instruction footprint down (ncu: stall_no_instruction dominated k_shade before).
+#define PSY_NOINLINE __device__ __noinline__
 
 namespace psyd {
 

@@ -118,7 +118,7 @@ PSY_DEV void sobol_sample_4d(uint32_t index, uint32_t dimension_set, uint32_t se
     }
 }
 // get_sample_4d (renderer.rs:698-725)
-PSY_DEV void get_sample_4d(uint32_t i, uint32_t dimension_set, uint32_t px, uint32_t py, uint32_t seed, float out[4]) {
+PSY_NOINLINE void get_sample_4d(uint32_t i, uint32_t dimension_set, uint32_t px, uint32_t py, uint32_t seed, float out[4]) {
     uint32_t s = px ^ (py << 16) ^ (seed * 0x736caf6fu);
     if (dimension_set < 2u) {
         sobol_sample_4d(i, dimension_set, s, out);
@@ -169,7 +169,7 @@ PSY_DEV float power_heuristic(float a, float b) {
 }
 
 //---- Monte-Carlo warps (monte_carlo.rs) ---------------------------------------------------------
-PSY_DEV void square_to_circle(float x, float y, float& ox, float& oy) {
+PSY_NOINLINE void square_to_circle(float x, float y, float& ox, float& oy) {
     const float QPI = 0.78539816339744830962f;
     if (x == 0.0f && y == 0.0f) {
         ox = 0.0f, oy = 0.0f;
@@ -206,7 +206,7 @@ PSY_DEV V3 uniform_sample_sphere(float u, float v) {
     float phi = 2.0f * PSY_PI_32 * v;
     return mk3(r * cosf(phi), r * sinf(phi), z);
 }
-PSY_DEV V3 uniform_sample_cone(float u, float v, double cos_theta_max) {
+PSY_NOINLINE V3 uniform_sample_cone(float u, float v, double cos_theta_max) {
     double cos_theta = (1.0 - (double)u) + ((double)u * cos_theta_max);
     double sin_theta = sqrt(1.0 - (cos_theta * cos_theta));
     double phi = (double)v * 2.0 * PSY_PI_64;
@@ -235,7 +235,7 @@ PSY_DEV SphTri sph_tri_edges(V3 va, V3 vb, V3 vc) {
     s.sin_c = sqrt(1.0 - (s.cos_c * s.cos_c));
     return s;
 }
-PSY_DEV float spherical_triangle_solid_angle(V3 va, V3 vb, V3 vc) {
+PSY_NOINLINE float spherical_triangle_solid_angle(V3 va, V3 vb, V3 vc) {
     SphTri s = sph_tri_edges(va, vb, vc);
     if (s.cos_a == 1.0 || s.cos_b == 1.0 || s.cos_c == 1.0) return 0.0f;
     double cos_va = rmin(rmax((s.cos_a - (s.cos_b * s.cos_c)) / (s.sin_b * s.sin_c), -1.0), 1.0);
@@ -244,7 +244,7 @@ PSY_DEV float spherical_triangle_solid_angle(V3 va, V3 vb, V3 vc) {
     double ang_va = acos(cos_va), ang_vb = acos(cos_vb), ang_vc = acos(cos_vc);
     return (float)(ang_va + ang_vb + ang_vc - PSY_PI_64);
 }
-PSY_DEV V3 uniform_sample_spherical_triangle(V3 va, V3 vb, V3 vc, float i, float j) {
+PSY_NOINLINE V3 uniform_sample_spherical_triangle(V3 va, V3 vb, V3 vc, float i, float j) {
     SphTri s = sph_tri_edges(va, vb, vc);
     if (s.cos_a == 1.0 || s.cos_b == 1.0 || s.cos_c == 1.0) return va;
     double cos_va = rmin(rmax((s.cos_a - (s.cos_b * s.cos_c)) / (s.sin_b * s.sin_c), -1.0), 1.0);
@@ -386,7 +386,7 @@ PSY_DEV float plancks_law_normalized(float temperature, float wavelength) {
     float t2 = temperature * temperature;
     return plancks_law(temperature, wavelength) * 4.0e7f / (t2 * t2);
 }
-PSY_DEV V4 color_to_spectral(const DScene& S, const PsyColor& c, float hero) {
+PSY_NOINLINE V4 color_to_spectral(const DScene& S, const PsyColor& c, float hero) {
     float wls[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) wls[i] = nth_wavelength(hero, i);
@@ -598,7 +598,7 @@ PSY_DEV void closure_sample(const Closure& cl, const ShadeCtx& sc, V3 inc, float
         pdf = 1.0f;
     }
 }
-PSY_DEV float sphere_lambert(float nlcos, float rcos) {
+PSY_NOINLINE float sphere_lambert(float nlcos, float rcos) {
     float nlsin = sqrtf(1.0f - (nlcos * nlcos));
     float rsin2 = 1.0f - (rcos * rcos);
     float rsin = sqrtf(rsin2);
@@ -693,7 +693,7 @@ PSY_DEV void surface_point(V3 t0, V3 t1, V3 t2, float b0, float b1, float b2, V3
     V3 e = (((vabs(t0) * b0) + (vabs(t1) * b1)) + (vabs(t2) * b2)) * fp_gamma(7);
     pos_err = max_element(e);
 }
-PSY_DEV float sphere_sample_pdf(const DScene& S, const PsyLight& l, const Xf& space, V3 arr, float time) {
+PSY_NOINLINE float sphere_sample_pdf(const DScene& S, const PsyLight& l, const Xf& space, V3 arr, float time) {
     V3 a = xf_point(space, arr);
     double radius = (double)lerp_slice_f(S.light_shape + l.shape_base, l.n_shape, time);
     double d2 = (double)length2(mk3(0, 0, 0) - a);
@@ -705,7 +705,7 @@ PSY_DEV float sphere_sample_pdf(const DScene& S, const PsyLight& l, const Xf& sp
     }
     return (float)(1.0 / (4.0 * PSY_PI_64));
 }
-PSY_DEV float rect_sample_pdf(const Xf& space_inv, float w, float h, V3 arr, V3 sample_dir, V3 hit_point) {
+PSY_NOINLINE float rect_sample_pdf(const Xf& space_inv, float w, float h, V3 arr, V3 sample_dir, V3 hit_point) {
     V3 p1, p2, p3, p4;
     rect_corners(space_inv, w, h, p1, p2, p3, p4);
     V3 sp1 = normalized(p1 - arr), sp2 = normalized(p2 - arr), sp3 = normalized(p3 - arr), sp4 = normalized(p4 - arr);
