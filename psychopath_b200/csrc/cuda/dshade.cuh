@@ -598,21 +598,23 @@ PSY_DEV void closure_sample(const Closure& cl, const ShadeCtx& sc, V3 inc, float
         pdf = 1.0f;
     }
 }
+// sphere_lambert (surface_closure.rs:346-377).  The reference evaluates g and h before branching; they
+// only feed the two partially-occluded cases, so they are evaluated there (pure functions: same bits).
 PSY_NOINLINE float sphere_lambert(float nlcos, float rcos) {
-    float nlsin = sqrtf(1.0f - (nlcos * nlcos));
     float rsin2 = 1.0f - (rcos * rcos);
+    float nl = acosf(nlcos);
+    float r = acosf(rcos);
+    if (nl < (PSY_H_PI - r)) return nlcos * rsin2;
+    if (!(nl < PSY_H_PI) && !(nl < (PSY_H_PI + r))) return 0.0f;
+    float nlsin = sqrtf(1.0f - (nlcos * nlcos));
     float rsin = sqrtf(rsin2);
     float ysin = rcos / nlsin;
     float ycos2 = 1.0f - (ysin * ysin);
     float ycos = sqrtf(ycos2);
     float g = (-2.0f * nlsin * rcos * ycos) + PSY_H_PI - asinf(ysin) + (ysin * ycos);
     float h = nlcos * ((ycos * sqrtf(rsin2 - ycos2)) + (rsin2 * asinf(ycos / rsin)));
-    float nl = acosf(nlcos);
-    float r = acosf(rcos);
-    if (nl < (PSY_H_PI - r)) return nlcos * rsin2;
     if (nl < PSY_H_PI) return (nlcos * rsin2) + g - h;
-    if (nl < (PSY_H_PI + r)) return (g + h) * PSY_INV_PI;
-    return 0.0f;
+    return (g + h) * PSY_INV_PI;
 }
 // The part of estimate_eval_over_sphere_light that does not depend on the light: evaluated once per
 // light-tree walk instead of once per child (same inputs, same bits).
@@ -995,13 +997,21 @@ PSY_DEV float distant_energy(const DScene& S, const PsyDistantLight& l) {
     return a / (float)l.n_colors;
 }
 
-// Scene::sample_lights + Assembly::sample_lights, recursion unrolled into a loop
-// (scene/mod.rs:28-99, scene/assembly.rs:46-140)
+// Scene::sample_lights + Assembly::sample_lights (scene/mod.rs:28-99, scene/assembly.rs:46-140) in two
+// halves so that the light-tree walk and the (f64-heavy) light sampling can live in different kernels:
+//   select_light        world/local choice, weighted_choice, LightTree::select through nested assemblies
+//   sample_picked_light DistantDiskLight / SphereLight / RectangleLight::sample_from_point
+struct LightPick {
+    uint32_t kind;         // 0 none, 1 distant light, 2 surface light
+    uint32_t index;        // distant: index into distant_lights; surface: global light_instances index
+    uint32_t parent_path;  // path of the assembly instance that contains the light (PSY_NONE = root)
+    float selection_pdf;
+};
 template <uint32_t KIND>
-__device__ __noinline__ void sample_lights(const DScene& S, float n, float u, float v, float wl, float time,
-                                           const Isect& intr, LightSample& out) {
+__device__ __noinline__ void select_light(const DScene& S, float n, float time, const Isect& intr, LightPick& out) {
     out.kind = 0;
-    out.pdf = 0.0f;
+    out.index = 0;
+    out.parent_path = PSY_NONE;
     out.selection_pdf = 0.0f;
     float wl_energy = S.world_light_energy_sum <= 0.0f ? 0.0f : 1.0f;
     float ll_energy = S.assemblies[S.root_assembly].light_energy <= 0.0f ? 0.0f : 1.0f;
@@ -1026,29 +1036,8 @@ __device__ __noinline__ void sample_lights(const DScene& S, float n, float u, fl
             }
         }
         if (pick == PSY_NONE) return;
-        // DistantDiskLight::sample_from_point (distant_disk_light.rs:59-85)
-        const PsyDistantLight l = S.distant_lights[pick];
-        double radius = (double)lerp_slice_f(S.world_floats + l.radii_base, l.n_radii, time);
-        V3 direction;
-        {
-            uint32_t i1;
-            float a2;
-            const float* dp = S.world_floats + l.dir_base;
-            if (!lerp_slice_keys(l.n_dirs, time, i1, a2))
-                direction = bbv(dp + 3 * i1);
-            else
-                direction = lerp3(bbv(dp + 3 * i1), bbv(dp + 3 * i1 + 3), a2);
-        }
-        PsyColor col = lerp_slice_color(S.light_colors + l.color_base, l.n_colors, time);
-        double solid_angle_inv = 1.0 / (2.0 * PSY_PI_64 * (1.0 - cos(radius)));
-        V3 z = -normalized(direction), x2, y2;
-        coordinate_system_from_vector(z, x2, y2);
-        double cos_theta_max = cos(radius);
-        V3 sample = normalized(uniform_sample_cone(u, v, cos_theta_max));
         out.kind = 1;
-        out.color = color_to_spectral(S, col, wl) * (float)solid_angle_inv;
-        out.direction = ((x2 * sample.x) + (y2 * sample.y)) + (z * sample.z);
-        out.pdf = (float)uniform_sample_cone_pdf(cos_theta_max);
+        out.index = pick;
         out.selection_pdf = p * wl_prob;
         return;
     }
@@ -1074,20 +1063,9 @@ __device__ __noinline__ void sample_lights(const DScene& S, float n, float u, fl
             return;
         const PsyInstance inst = S.light_instances[a.light_instance_base + light_i];
         if (inst.kind == PSY_INSTANCE_OBJECT) {
-            const PsyObject o = S.objects[inst.data_index];
-            const PsyLight l = S.lights[o.index];
-            Xf xform;
-            if (inst.xform_count > 0) {
-                Xf own = lerp_slice_xf(S.xforms + 3 * (size_t)inst.xform_base, inst.xform_count, time);
-                xform = have_parent ? xf_mul(sel_xform, own) : own;
-            } else {
-                xform = sel_xform;
-            }
             out.kind = 2;
-            if (l.kind == PSY_LIGHT_SPHERE)
-                sample_sphere_light(S, l, xform, intr.pos, u, v, wl, time, out);
-            else
-                sample_rect_light(S, l, xform, intr.pos, u, v, wl, time, out);
+            out.index = a.light_instance_base + light_i;
+            out.parent_path = cur_path;
             float sp = sel_pdf;
             // sample.map(|..spdf| spdf * sel_pdf) applied from the innermost level outwards
             for (int k = depth - 1; k >= 0; --k) sp = sp * sel_chain[k];
@@ -1102,6 +1080,57 @@ __device__ __noinline__ void sample_lights(const DScene& S, float n, float u, fl
         path_base = S.paths[cur_path].child_base;
         asm_index = inst.data_index;
         nn = whittled_n;
+    }
+}
+
+__device__ __noinline__ void sample_picked_light(const DScene& S, const LightPick& pick, float u, float v, float wl,
+                                                 float time, V3 pos, LightSample& out) {
+    out.kind = 0;
+    out.pdf = 0.0f;
+    out.selection_pdf = pick.selection_pdf;
+    if (pick.kind == 1u) {
+        // DistantDiskLight::sample_from_point (distant_disk_light.rs:59-85)
+        const PsyDistantLight l = S.distant_lights[pick.index];
+        double radius = (double)lerp_slice_f(S.world_floats + l.radii_base, l.n_radii, time);
+        V3 direction;
+        {
+            uint32_t i1;
+            float a2;
+            const float* dp = S.world_floats + l.dir_base;
+            if (!lerp_slice_keys(l.n_dirs, time, i1, a2))
+                direction = bbv(dp + 3 * i1);
+            else
+                direction = lerp3(bbv(dp + 3 * i1), bbv(dp + 3 * i1 + 3), a2);
+        }
+        PsyColor col = lerp_slice_color(S.light_colors + l.color_base, l.n_colors, time);
+        double solid_angle_inv = 1.0 / (2.0 * PSY_PI_64 * (1.0 - cos(radius)));
+        V3 z = -normalized(direction), x2, y2;
+        coordinate_system_from_vector(z, x2, y2);
+        double cos_theta_max = cos(radius);
+        V3 sample = normalized(uniform_sample_cone(u, v, cos_theta_max));
+        out.kind = 1;
+        out.color = color_to_spectral(S, col, wl) * (float)solid_angle_inv;
+        out.direction = ((x2 * sample.x) + (y2 * sample.y)) + (z * sample.z);
+        out.pdf = (float)uniform_sample_cone_pdf(cos_theta_max);
+    } else if (pick.kind == 2u) {
+        // the light instance's world->object transform (assembly.rs:77-97)
+        const PsyInstance inst = S.light_instances[pick.index];
+        const PsyObject o = S.objects[inst.data_index];
+        const PsyLight l = S.lights[o.index];
+        bool have_parent = pick.parent_path != PSY_NONE && S.paths[pick.parent_path].xf_count > 0;
+        Xf sel_xform = have_parent ? path_xform(S, S.paths[pick.parent_path], time) : xf_identity();
+        Xf xform;
+        if (inst.xform_count > 0) {
+            Xf own = lerp_slice_xf(S.xforms + 3 * (size_t)inst.xform_base, inst.xform_count, time);
+            xform = have_parent ? xf_mul(sel_xform, own) : own;
+        } else {
+            xform = sel_xform;
+        }
+        out.kind = 2;
+        if (l.kind == PSY_LIGHT_SPHERE)
+            sample_sphere_light(S, l, xform, pos, u, v, wl, time, out);
+        else
+            sample_rect_light(S, l, xform, pos, u, v, wl, time, out);
     }
 }
 

@@ -17,8 +17,6 @@ namespace psyd {
 // (tracer.rs:131-148 calls update_local again; same inputs, same bits).
 constexpr int CTX_WORDS = 10;
 
-PSY_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 struct TraversalMem {
     uint32_t stack[TRACE_STACK_SIZE];
     uint32_t ctx[CTX_WORDS * (TRACE_MAX_NEST + 1)];  // the last slot belongs to the mesh level
@@ -228,17 +226,9 @@ struct Traversal {
                 const uint32_t lo = (child_i & 1u) ? child.y : child.x;
                 const uint32_t hi = (child_i & 1u) ? child.w : child.z;
                 const uint32_t c = (child_i & 2u) ? hi : lo;
-                if ((uint32_t)i < meta.w && ((hits >> child_i) & 1u)) {
-                    stack[sp++] = c;
-                    // The pushed entry is popped a few iterations from now: start pulling its 128-byte
-                    // node record (or the first triangle of a leaf) towards L1 now.
-                    if (!(c & PSY_CHILD_LEAF_BIT)) {
-                        prefetch_l1(S.nodes + (size_t)c * 8u);
-                    } else if (in_mesh) {
-                        prefetch_l1(S.tri_verts + mesh_tv_base +
-                                    (size_t)(PSY_CHILD_LEAF_START(c) - mesh_tri_base) * 3u * mesh_n_keys);
-                    }
-                }
+                // (prefetch.global.L1 of the pushed children was tried here: 8 % slower on B200 — the
+                // kernel is issue-bound, not latency-bound, see profiles/README.md.)
+                if ((uint32_t)i < meta.w && ((hits >> child_i) & 1u)) stack[sp++] = c;
             }
         }
     }

@@ -37,6 +37,8 @@ struct PathPool {
     float4* pending;
     float4* color;
     HitRec* hits;
+    uint4* light_pick;  // k_shade_select -> k_shade: LightPick (kind, index, parent path, selection pdf)
+    float2* light_uv;   // the two light-sampling random numbers of the same Sobol vector
 };
 
 struct Bucket {
@@ -328,10 +330,15 @@ PSY_DEV bool path_next(const DScene& S, const PathPool& P, uint32_t slot, const 
     uint32_t q = slot / b.spp, si = slot - q * b.spp;
     uint32_t px = b.x + (q % b.w), py = b.y + (q / b.w);
     sseed += 1u;
-    float s4[4];
-    get_sample_4d(si, 0, px, py, sseed, s4);
+    // The light was chosen by k_shade_select (light-tree walk); here it is sampled.
+    LightPick pick;
+    {
+        const uint4 lp = P.light_pick[slot];
+        pick.kind = lp.x, pick.index = lp.y, pick.parent_path = lp.z, pick.selection_pdf = __uint_as_float(lp.w);
+    }
+    const float2 luv = P.light_uv[slot];
     LightSample li;
-    sample_lights<KIND>(S, s4[0], s4[1], s4[2], wl, time, is, li);
+    sample_picked_light(S, pick, luv.x, luv.y, wl, time, is.pos, li);
     bool found_light = false;
     if (!(li.kind == 0 || li.pdf <= 0.0f || li.selection_pdf <= 0.0f)) {
         V4 attenuation;
@@ -408,6 +415,32 @@ PSY_DEV bool path_next(const DScene& S, const PathPool& P, uint32_t slot, const 
     P.flags[slot] = flags;
     P.light_atten[slot] = to_f4(light_attenuation);
     return false;
+}
+
+// First half of a surface hit (classes LAMBERT / GGX): the light-tree walk of Scene::sample_lights.  It is
+// its own kernel so that this loop-heavy, small piece of code is not evicted from the instruction cache by
+// the f64 light-sampling and spectral code of k_shade (k_shade<LAMBERT> was stalled on instruction fetch
+// for 12 of 17 cycles per issue when it contained both, profiles/r1_shade_lambert_r1g.txt).
+template <int CLS>
+__global__ void __launch_bounds__(128) k_shade_select(DScene S, PathPool P, Bucket b, ShadeQueues Q) {
+    constexpr uint32_t KIND = CLS == SHADE_LAMBERT ? (uint32_t)PSY_SHADER_LAMBERT : (uint32_t)PSY_SHADER_GGX;
+    const uint32_t n = Q.count[CLS];
+    const uint32_t* __restrict__ queue = Q.q[CLS];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = queue[i];
+        const HitRec h = P.hits[slot];
+        const float4 ro = P.ray_o[slot], rd = P.ray_d[slot];
+        Isect is;
+        finalize_hit(S, h, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), ro.w, is);
+        const uint32_t q = slot / b.spp, si = slot - q * b.spp;
+        const uint32_t px = b.x + (q % b.w), py = b.y + (q / b.w);
+        float s4[4];
+        get_sample_4d(si, 0, px, py, P.sseed[slot] + 1u, s4);  // next_lds_sequence(); next_lds_samp()
+        LightPick pick;
+        select_light<KIND>(S, s4[0], ro.w, is, pick);
+        P.light_pick[slot] = make_uint4(pick.kind, pick.index, pick.parent_path, __float_as_uint(pick.selection_pdf));
+        P.light_uv[slot] = make_float2(s4[1], s4[2]);
+    }
 }
 
 // One launch per shading class; survivors of all classes are appended to the next wave's live list.

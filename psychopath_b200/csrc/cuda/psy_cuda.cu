@@ -77,7 +77,7 @@ struct PsyScene {
     // path pool
     size_t pool_cap = 0;
     DevBuf pool_ray_o, pool_ray_d, pool_flags, pool_sseed, pool_wl, pool_cpdf, pool_nb_o, pool_nb_d, pool_next_atten,
-        pool_light_atten, pool_pending, pool_color, pool_hits, active_a, active_b;
+        pool_light_atten, pool_pending, pool_color, pool_hits, pool_light_pick, pool_light_uv, active_a, active_b;
     DevBuf counts, fetch, qcounts, queues, counters, image, bucket_out, samples_out;
     size_t counts_cap = 0;
     std::vector<cudaEvent_t> events;
@@ -206,6 +206,8 @@ PathPool make_pool(PsyScene* sc) {
     P.pending = sc->pool_pending.as<float4>();
     P.color = sc->pool_color.as<float4>();
     P.hits = sc->pool_hits.as<HitRec>();
+    P.light_pick = sc->pool_light_pick.as<uint4>();
+    P.light_uv = sc->pool_light_uv.as<float2>();
     return P;
 }
 
@@ -225,6 +227,8 @@ int32_t ensure_pool(PsyScene* sc, size_t n) {
     CK(sc->pool_pending.alloc(cap * 16));
     CK(sc->pool_color.alloc(cap * 16));
     CK(sc->pool_hits.alloc(cap * sizeof(HitRec)));
+    CK(sc->pool_light_pick.alloc(cap * 16));
+    CK(sc->pool_light_uv.alloc(cap * 8));
     CK(sc->active_a.alloc(cap * 4));
     CK(sc->active_b.alloc(cap * 4));
     CK(sc->queues.alloc(cap * 4 * SHADE_CLASSES));
@@ -307,10 +311,12 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
         uint32_t* next_count = counts + w + 1;
         k_shade<SHADE_SIMPLE><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
         k_shade<SHADE_EMIT><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
+        k_shade_select<SHADE_LAMBERT><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q);
         k_shade<SHADE_LAMBERT><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
+        k_shade_select<SHADE_GGX><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q);
         k_shade<SHADE_GGX><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
         stamp(ev ? &ev->shade : nullptr, false);
-        *launches += 5;
+        *launches += 7;
     }
     stamp(ev ? &ev->film : nullptr, true);
     k_film<<<(b.w * b.h + 127) / 128, 128, 0, st>>>(P, b, out, stride, ox, oy, samples_out);
