@@ -130,13 +130,17 @@ def algorithmic_bytes_per_ray(st, keys_node=1.0, keys_vert=1, keys_xform=1):
 def cpu_sample(scene, spp, seed, target_s=15.0, threads=0):
     """Times the oracle on a bounded number of Hilbert-ordered buckets of the same workload."""
     import oracle_lib as O
-    nb = 64
-    _, st, done = O.render_image(scene.desc, spp, seed, spb=4096, threads=threads, max_buckets=nb)
-    rate = st.ray_count / max(st.total_time, 1e-9)
-    if st.total_time < target_s * 0.5:
-        nb = int(min(max(nb * target_s / max(st.total_time, 1e-3), nb), 1 << 22))
+    # Buckets are drawn evenly from the whole Hilbert list (oracle_render_image), so the rate of a small
+    # probe extrapolates; grow the sample until it takes about target_s (at most 3 rounds, bounded).
+    ncores = os.cpu_count() or 1
+    nb = 8 * ncores
+    for _ in range(3):
         _, st, done = O.render_image(scene.desc, spp, seed, spb=4096, threads=threads, max_buckets=nb)
-        rate = st.ray_count / max(st.total_time, 1e-9)
+        if st.total_time >= 0.5 * target_s:
+            break
+        grow = min(max(0.9 * target_s / max(st.total_time, 1e-3), 1.5), 16.0)
+        nb = int(nb * grow)
+    rate = st.ray_count / max(st.total_time, 1e-9)
     return {"mrays_s": rate / 1e6, "msamples_s": st.samples / max(st.total_time, 1e-9) / 1e6, "seconds": st.total_time,
             "buckets": done, "rays": int(st.ray_count), "samples": int(st.samples), "threads": int(st.threads)}
 
@@ -283,27 +287,47 @@ def main():
     value = rays / dev_s / 1e6
     msamples = samples_per_step * args.steps / dev_s / 1e6
 
-    # ---- end-to-end through the C ABI with host buffers (rank-local; N=1 figure is the headline) ----
+    # ---- end-to-end through the C ABI with host buffers: every step each rank uploads the scene description
+    # (H2D), renders its tiles, the tiles are gathered, and rank 0 reads the finished image back (D2H) ----
+    def e2e_step():
+        rr = api.Renderer(scene, device=local_rank)          # H2D: the whole scene description
+        if world == 1:
+            img_, st_ = rr.render(max_samples_per_bucket=args.pool)   # D2H: the finished image
+        else:
+            st_ = rr.render_shard(rank, world, max_samples_per_bucket=args.pool)
+            ptr_, n_ = rr.device_image()
+
+            class _W:
+                __cuda_array_interface__ = {"shape": (n_,), "typestr": "<f4", "data": (ptr_, False), "version": 2}
+            t_ = torch.as_tensor(_W(), device=torch.device("cuda", local_rank))
+            dist.reduce(t_, dst=0, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize()
+            img_ = rr.fetch_image() if rank == 0 else None          # D2H on rank 0
+        rr.close()
+        return img_, st_
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e_rays = 0
+    n_e2e = max(1, min(args.steps, 2))
+    for _ in range(n_e2e):
+        img, st2 = e2e_step()
+        e_rays += int(st2["ray_count"])
+    barrier()
+    e_s = time.perf_counter() - t0
+    et = torch.tensor([e_s, float(e_rays)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        emax = et.clone()
+        dist.all_reduce(emax, op=dist.ReduceOp.MAX)
+        esum = et.clone()
+        dist.all_reduce(esum, op=dist.ReduceOp.SUM)
+        e_s, e_rays = float(emax[0]), int(esum[1])
     e2e = None
-    if world == 1:
-        def e2e_step():
-            rr = api.Renderer(scene, device=local_rank)      # H2D: the whole scene description
-            img, st2 = rr.render(max_samples_per_bucket=args.pool)  # D2H: the finished image
-            rr.close()
-            return img, st2
-        e2e_step()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e_rays = 0
-        n_e2e = max(1, min(args.steps, 2))
-        for _ in range(n_e2e):
-            img, st2 = e2e_step()
-            e_rays += int(st2["ray_count"])
-        torch.cuda.synchronize()
-        e_s = time.perf_counter() - t0
-        e2e = {"value": e_rays / e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(scene.host_bytes()),
+    if rank == 0:
+        e2e = {"value": e_rays / e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(scene.host_bytes()) * world,
                "d2h_bytes_per_step": int(rx * ry * 12), "steps": n_e2e, "ms_per_step": e_s / n_e2e * 1e3,
-               "image_mean_xyz": [float(x) for x in img.reshape(-1, 3).mean(axis=0)]}
+               "image_mean_xyz": [float(x) for x in np.nanmean(np.where(np.isfinite(img), img, np.nan).reshape(-1, 3), axis=0)],
+               "non_finite_pixels": int((~np.isfinite(img).all(axis=-1)).sum())}
 
     # ---- roofline of k_trace: visit counts from the counters build at reduced spp (per-ray averages) ----
     roofline = None

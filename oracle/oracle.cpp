@@ -1328,7 +1328,8 @@ int oracle_render_bucket(const PsySceneDesc* d, uint32_t x, uint32_t y, uint32_t
 
 // Renderer::render (renderer.rs:76-191): Hilbert-ordered buckets over `threads` workers.
 // crop = (x1,y1,x2,y2) inclusive or NULL.  xyz_out: res_x*res_y*3 (row 0 = top).
-// max_buckets > 0 stops after that many buckets (bounded CPU-baseline sample); buckets_done reports it.
+// max_buckets > 0 renders only that many buckets, spread evenly over the Hilbert-ordered list (bounded
+// CPU-baseline sample); buckets_done reports how many were rendered.
 int oracle_render_image(const PsySceneDesc* d, const uint32_t* crop, uint32_t spp, uint32_t seed, uint32_t spb,
                         uint32_t threads, uint32_t max_buckets, float* xyz_out, OracleStats* st, uint32_t* buckets_done) {
     Paths paths = expand_paths(*d);
@@ -1361,7 +1362,13 @@ int oracle_render_image(const PsySceneDesc* d, const uint32_t* crop, uint32_t sp
             if (w > 0 && h > 0) jobs.push_back({start_x + (uint32_t)x, start_y + (uint32_t)y, w, h});
         }
     }
-    if (max_buckets > 0 && jobs.size() > max_buckets) jobs.resize(max_buckets);
+    if (max_buckets > 0 && jobs.size() > max_buckets) {
+        // bounded sample: every k-th bucket of the Hilbert list, so the sample covers the whole image
+        // (the first N buckets alone would be one corner of it)
+        std::vector<Job> picked(max_buckets);
+        for (uint32_t i = 0; i < max_buckets; ++i) picked[i] = jobs[(size_t)i * jobs.size() / max_buckets];
+        jobs.swap(picked);
+    }
     if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
     std::atomic<size_t> next{0};
     std::vector<BucketResult> results(threads);

@@ -289,7 +289,7 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
     uint32_t shade_blocks = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 16);
     ShadeQueues Q;
     static const TraceTuning tune = [] {
-        TraceTuning t{64, 8, 8};  // measured best on the C4 scene (profiles/README.md)
+        TraceTuning t{64, 12, 8};  // measured best on the C4 scene (profiles/README.md)
         if (const char* e = getenv("PSY_TRACE_LEAFMIN")) t.leaf_min = atoi(e);
         if (const char* e = getenv("PSY_TRACE_BUDGET")) t.step_budget = atoi(e);
         if (const char* e = getenv("PSY_TRACE_REFILL")) t.refill_min = atoi(e);
