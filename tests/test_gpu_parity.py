@@ -172,3 +172,35 @@ def test_edge_cases():
     oh, _, _ = O.trace_rays(scene.desc, rays)
     assert np.array_equal(gh["kind"], oh["kind"])
     assert gh["kind"][1] == abi.HIT_MISS and gh["kind"][2] == abi.HIT_MISS
+
+
+def test_cli_drop_in(tmp_path):
+    """The `psychopath` CLI (bin/psychopath) renders the shipped example scene unchanged and speaks the
+    Blender stream protocol of src/renderer.rs:332-340."""
+    import base64
+    import os
+    import subprocess
+    import cv2
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(repo, "bin", "psychopath")
+    scene = os.path.join(repo, "tests", "golden", "cube.psy")
+    (tmp_path / "test_renders").mkdir()
+    out = subprocess.run([exe, "-i", scene, "--spp", "4", "--stats"], cwd=tmp_path, capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "Rays traced:" in out.stdout and "Writing image to disk into 'test_renders/cube.png'" in out.stdout
+    img = cv2.imread(str(tmp_path / "test_renders" / "cube.png"))
+    assert img is not None and img.shape[:2] == (540, 960) and img.mean() > 5
+    # stdin + serialized output, as PsychoBlend drives it (psychoblend/render.py:37-63,191-230)
+    text = open(scene).read() + "\n__PSY_EOF__\n"
+    out = subprocess.run([exe, "--spb", "65536", "--serialized_output", "--use_stdin", "--spp", "1"], cwd=tmp_path,
+                         input=text, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    blocks = out.stdout.split("BUCKET_END")
+    assert len(blocks) > 2
+    lines = [l for l in blocks[0].split("\n") if l.strip()]
+    i = lines.index("DIV")
+    assert lines[i + 1].endswith("%")
+    x0, y0, x1, y1 = [int(v) for v in lines[i + 2].split()]
+    data = np.frombuffer(base64.b64decode(lines[i + 3]), dtype=np.float32)
+    assert data.size == (x1 - x0) * (y1 - y0) * 4 and (data[3::4] == 1.0).all()
