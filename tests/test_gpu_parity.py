@@ -196,11 +196,11 @@ def test_cli_drop_in(tmp_path):
     out = subprocess.run([exe, "--spb", "65536", "--serialized_output", "--use_stdin", "--spp", "1"], cwd=tmp_path,
                          input=text, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
-    blocks = out.stdout.split("BUCKET_END")
+    # the reference prints "0.00%" without newline first (renderer.rs:133), so the stream is split on "DIV\n"
+    blocks = [b for b in out.stdout.split("DIV\n") if "BUCKET_END" in b]
     assert len(blocks) > 2
-    lines = [l for l in blocks[0].split("\n") if l.strip()]
-    i = lines.index("DIV")
-    assert lines[i + 1].endswith("%")
-    x0, y0, x1, y1 = [int(v) for v in lines[i + 2].split()]
-    data = np.frombuffer(base64.b64decode(lines[i + 3]), dtype=np.float32)
+    lines = blocks[0].split("\n")
+    assert lines[0].endswith("%") and lines[3] == "BUCKET_END"
+    x0, y0, x1, y1 = [int(v) for v in lines[1].split()]
+    data = np.frombuffer(base64.b64decode(lines[2]), dtype=np.float32)
     assert data.size == (x1 - x0) * (y1 - y0) * 4 and (data[3::4] == 1.0).all()
