@@ -791,7 +791,7 @@ __device__ __noinline__ void finalize_hit(const DScene& S, const HitRec& h, V3 o
         const PsyLight l = S.lights[obj.index];
         Xf xform = path_xform(S, P, time);
         float w, hh;
-        rect_dims(S, l, time, w, hh);
+        rect_dims(S.light_shape, l, time, w, hh);
         Xf space_inv = xf_inverse(xform);
         V3 p1, p2, p3, p4;
         rect_corners(space_inv, w, hh, p1, p2, p3, p4);
@@ -943,7 +943,7 @@ __device__ __noinline__ void sample_sphere_light(const DScene& S, const PsyLight
 __device__ __noinline__ void sample_rect_light(const DScene& S, const PsyLight& l, const Xf& space, V3 arr, float u,
                                                float v, float wl, float time, LightSample& out) {
     float w, h;
-    rect_dims(S, l, time, w, h);
+    rect_dims(S.light_shape, l, time, w, h);
     PsyColor col = lerp_slice_color(S.light_colors + l.color_base, l.n_colors, time);
     double surface_area = (double)w * (double)h;
     double surface_area_inv = 1.0 / surface_area;

@@ -154,8 +154,8 @@ PSY_DEV Xf path_mat_space(const DScene& S, const DPath& P, uint32_t p, float tim
 PSY_DEV int ray_code(V3 d) { return (d.x < 0.0f ? 1 : 0) + (d.y < 0.0f ? 2 : 0) + (d.z < 0.0f ? 4 : 0); }
 
 // Rectangle-light dimensions at `time` (lerp of (w,h) tuples)
-PSY_DEV void rect_dims(const DScene& S, const PsyLight& l, float time, float& w, float& h) {
-    const float* s = S.light_shape + l.shape_base;
+PSY_DEV void rect_dims(const float* __restrict__ light_shape, const PsyLight& l, float time, float& w, float& h) {
+    const float* s = light_shape + l.shape_base;
     uint32_t i1;
     float a2;
     if (!lerp_slice_keys(l.n_shape, time, i1, a2)) {
@@ -168,9 +168,9 @@ PSY_DEV void rect_dims(const DScene& S, const PsyLight& l, float time, float& w,
 }
 
 // SphereLight hit test (sphere_light.rs:214-280); returns true and t on a hit
-PSY_DEV bool sphere_light_hit(const DScene& S, const PsyLight& l, const Xf& xform, V3 orig_local, V3 world_dir,
-                              float time, float max_t, float& t_out) {
-    float radius = lerp_slice_f(S.light_shape + l.shape_base, l.n_shape, time);
+PSY_DEV bool sphere_light_hit(const float* __restrict__ light_shape, const PsyLight& l, const Xf& xform, V3 orig_local,
+                              V3 world_dir, float time, float max_t, float& t_out) {
+    float radius = lerp_slice_f(light_shape + l.shape_base, l.n_shape, time);
     V3 dir = xf_vector(xform, world_dir);
     float a = length2(dir);
     float b = 2.0f * dot(dir, orig_local);
@@ -205,5 +205,51 @@ PSY_DEV void rect_corners(const Xf& space_inv, float w, float h, V3& p1, V3& p2,
     p4 = xf_point(space_inv, mk3(w * 0.5f, h * -0.5f, 0.0f));
 }
 
+// Hit test of a ray against one light instance (sphere_light.rs:214-280, rectangle_light.rs:287-331),
+// out of line: light entries are a small share of the instance visits, and keeping their code (an
+// inverse, two watertight triangle tests with f64 fallback, a sqrt) away from the mesh / assembly
+// entry keeps the hot loop of k_trace compact in the instruction cache.
+struct LightHit {
+    uint32_t kind;  // PSY_HIT_MISS when nothing closer than max_t was hit
+    uint32_t prim;
+    float t, b0, b1, b2;
+    uint32_t tri_tests;
+};
+PSY_NOINLINE LightHit light_instance_hit(const PsyLight* __restrict__ lights, const float* __restrict__ light_shape,
+                                         uint32_t light_index, uint32_t path_kind, Xf xform, V3 orig, V3 dir,
+                                         V3 orig_in_space, float time, float max_t, RayTriPre pre) {
+    LightHit out;
+    out.kind = PSY_HIT_MISS, out.prim = 0, out.t = 0.0f, out.b0 = out.b1 = out.b2 = 0.0f, out.tri_tests = 0;
+    const PsyLight l = lights[light_index];
+    if (path_kind == PATH_SPHERE_LIGHT) {
+        float t;
+        if (sphere_light_hit(light_shape, l, xform, orig_in_space, dir, time, max_t, t)) {
+            out.kind = PSY_HIT_SPHERE_LIGHT;
+            out.t = t;
+        }
+    } else {
+        float w, h;
+        rect_dims(light_shape, l, time, w, h);
+        Xf space_inv = xf_inverse(xform);
+        V3 p1, p2, p3, p4;
+        rect_corners(space_inv, w, h, p1, p2, p3, p4);
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
+            V3 a = k == 0 ? p1 : p3, b = k == 0 ? p2 : p4, c = k == 0 ? p3 : p1;
+            float t, b0, b1, b2;
+            out.tri_tests += 1;
+            if (tri_intersect(orig, pre, max_t, a, b, c, t, b0, b1, b2)) {
+                if (t < max_t) {
+                    out.kind = PSY_HIT_RECT_LIGHT;
+                    out.t = t;
+                    out.prim = (uint32_t)k;
+                    out.b0 = b0, out.b1 = b1, out.b2 = b2;
+                    break;
+                }
+            }
+        }
+    }
+    return out;
+}
 
 }  // namespace psyd

@@ -77,7 +77,7 @@ struct Traversal {
         uint32_t* c = ctx + level * CTX_WORDS;
         c[0] = path_base;
         c[1] = asm_inst_base;
-        c[2] = own | (finite_dir_inv ? 2u : 0u);
+        c[2] = own | (finite_dir_inv ? 2u : 0u) | (octant << 2);
         c[3] = __float_as_uint(orig_local.x), c[4] = __float_as_uint(orig_local.y), c[5] = __float_as_uint(orig_local.z);
         c[6] = __float_as_uint(dir_inv_local.x), c[7] = __float_as_uint(dir_inv_local.y);
         c[8] = __float_as_uint(dir_inv_local.z);
@@ -90,7 +90,7 @@ struct Traversal {
             finite_dir_inv = (c[2] & 2u) != 0u;
             orig_local = mk3(__uint_as_float(c[3]), __uint_as_float(c[4]), __uint_as_float(c[5]));
             dir_inv_local = mk3(__uint_as_float(c[6]), __uint_as_float(c[7]), __uint_as_float(c[8]));
-            octant = (uint32_t)ray_code(dir_inv_local);
+            octant = c[2] >> 2;
         }
     }
 
@@ -220,54 +220,64 @@ struct Traversal {
             // push far -> near: order position i = n-1 .. 0, so position 0 is popped first (bvh4.rs:152-165).
             // Fully unrolled and predicated: every lane runs the same four slots.
             const uint32_t order_code = c_traversal_table[octant][meta.x];
+#ifdef PSY_PREFETCH_TOP
+            uint32_t next_ref = PSY_NONE;
+#endif
 #pragma unroll
             for (int i = 3; i >= 0; --i) {
                 const uint32_t child_i = (order_code >> (i * 2)) & 3u;
                 const uint32_t lo = (child_i & 1u) ? child.y : child.x;
                 const uint32_t hi = (child_i & 1u) ? child.w : child.z;
                 const uint32_t c = (child_i & 2u) ? hi : lo;
-                // (prefetch.global.L1 of the pushed children was tried here: 8 % slower on B200 — the
-                // kernel is issue-bound, not latency-bound, see profiles/README.md.)
-                if ((uint32_t)i < meta.w && ((hits >> child_i) & 1u)) stack[sp++] = c;
+                // (prefetch.global.L1 of all pushed children was tried here: 8 % slower on B200, see
+                // profiles/README.md.)
+                if ((uint32_t)i < meta.w && ((hits >> child_i) & 1u)) {
+                    stack[sp++] = c;
+#ifdef PSY_PREFETCH_TOP
+                    next_ref = c;
+#endif
+                }
             }
+#ifdef PSY_PREFETCH_TOP
+            // the entry that will be popped next: start its cache line(s) on the way while the warp runs
+            // the leaf phases and the loop bookkeeping
+            if (!(next_ref & PSY_CHILD_LEAF_BIT)) {
+                const char* a = reinterpret_cast<const char*>(S.nodes + (size_t)next_ref * 8u);
+#pragma unroll
+                for (int k = 0; k < PSY_PREFETCH_TOP; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 128 / PSY_PREFETCH_TOP * k));
+            }
+#endif
         }
     }
 
-    // ---- triangle leaf (triangle_mesh.rs:174-262); returns true when an occlusion ray is done
-    PSY_DEV bool visit_triangles(const DScene& S, uint32_t start, uint32_t count, TraceCounters& cnt) {
-        for (uint32_t ti = start; ti < start + count; ++ti) {
-            V3 p0, p1, p2;
-            load_tri_verts(S, ti, p0, p1, p2);
-            if (!space_empty) {
-                p0 = xf_point(mat_space, p0);
-                p1 = xf_point(mat_space, p1);
-                p2 = xf_point(mat_space, p2);
-            } else {
-                p0 = permute3(p0, pre), p1 = permute3(p1, pre), p2 = permute3(p2, pre);
+    // ---- one triangle of a leaf (triangle_mesh.rs:174-262); returns true when an occlusion ray is done.
+    // A leaf with several triangles stays parked and is consumed one triangle per flush, in order, so
+    // that every lane of a flush runs the same straight-line code.
+    PSY_DEV bool visit_triangle(const DScene& S, uint32_t ti, TraceCounters& cnt) {
+        V3 p0, p1, p2;
+        load_tri_verts(S, ti, p0, p1, p2);
+        if (!space_empty) {
+            p0 = xf_point(mat_space, p0);
+            p1 = xf_point(mat_space, p1);
+            p2 = xf_point(mat_space, p2);
+        } else {
+            p0 = permute3(p0, pre), p1 = permute3(p1, pre), p2 = permute3(p2, pre);
+        }
+        if (COUNT) cnt.tri_tests += 1;
+        float t, b0, b1, b2;
+        if (tri_intersect_perm(orig_p, pre, max_t, p0, p1, p2, t, b0, b1, b2)) {
+            if (occlusion) {
+                hit.kind = PSY_HIT_OCCLUDED;
+                return true;
             }
-            if (COUNT) cnt.tri_tests += 1;
-            float t, b0, b1, b2;
-            if (tri_intersect_perm(orig_p, pre, max_t, p0, p1, p2, t, b0, b1, b2)) {
-                if (occlusion) {
-                    hit.kind = PSY_HIT_OCCLUDED;
-                    return true;
-                }
-                max_t = t;
-                hit.kind = PSY_HIT_TRIANGLE;
-                hit.t = t;
-                hit.prim = ti;
-                hit.path = mesh_path;
-                hit.b0 = b0, hit.b1 = b1, hit.b2 = b2;
-            }
+            max_t = t;
+            hit.kind = PSY_HIT_TRIANGLE;
+            hit.t = t;
+            hit.prim = ti;
+            hit.path = mesh_path;
+            hit.b0 = b0, hit.b1 = b1, hit.b2 = b2;
         }
         return false;
-    }
-
-    // world->local transform of path p at the ray's time, from the flattened path record
-    PSY_DEV Xf rec_xform(const DScene& S, uint32_t p, uint32_t xf_count, uint32_t xf_base) const {
-        if (xf_count == 1u) return xf_load(S.path_static + 6 * (size_t)p);
-        if (xf_count == 0u) return xf_identity();
-        return lerp_slice_xf(S.path_xforms + 3 * (size_t)xf_base, xf_count, time);
     }
 
     // ---- instance (tracer.rs:94-149); assembly leaves hold exactly one instance.  Everything the entry
@@ -281,78 +291,54 @@ struct Traversal {
         const uint32_t own = (r0.x >> 3) & 1u;
         const uint32_t xf_count = r0.x >> 8;
         if (COUNT) cnt.instance_visits += 1;
-        if (kind == PATH_MESH) {
-            save_ctx(TRACE_MAX_NEST, own);
-            mesh_tri_base = r1.y, mesh_tv_base = r1.z, mesh_n_keys = r1.w;
-            mesh_path = p;
-            space_empty = xf_count == 0u;
-            if (xf_count == 1u) {
-                if (own) set_local(xf_load(S.path_static + 6 * (size_t)p));
-                mat_space = xf_permuted(xf_load(S.path_static + 6 * (size_t)p + 3));
-            } else if (xf_count > 1u) {
-                // transform motion blur: lerp the two keys around the ray's time, invert per ray in
-                // registers (triangle_mesh.rs:183-189)
-                Xf x = lerp_slice_xf(S.path_xforms + 3 * (size_t)r0.y, xf_count, time);
-                if (own) set_local(x);
-                mat_space = xf_permuted(xf_inverse(x));
+        // world->local transform of the instance at the ray's time: shared by every kind, so the lanes of a
+        // flush run it together whatever they are entering
+        Xf xform = xf_identity();
+        if (xf_count == 1u) {
+            xform = xf_load(S.path_static + 6 * (size_t)p);
+        } else if (xf_count > 1u) {
+            xform = lerp_slice_xf(S.path_xforms + 3 * (size_t)r0.y, xf_count, time);
+        }
+        if (kind == PATH_MESH || kind == PATH_ASSEMBLY) {
+            const bool mesh = kind == PATH_MESH;
+            if (!mesh && ctx_n >= TRACE_MAX_NEST) return false;
+            save_ctx(mesh ? TRACE_MAX_NEST : ctx_n, own);
+            if (own) set_local(xform);
+            if (mesh) {
+                mesh_tri_base = r1.y, mesh_tv_base = r1.z, mesh_n_keys = r1.w;
+                mesh_path = p;
+                space_empty = xf_count == 0u;
+                // local->world for the vertices: precomputed for static paths, else the inverse of the
+                // lerped keys, per ray in registers (triangle_mesh.rs:183-189)
+                if (xf_count == 1u) {
+                    mat_space = xf_permuted(xf_load(S.path_static + 6 * (size_t)p + 3));
+                } else if (xf_count > 1u) {
+                    mat_space = xf_permuted(xf_inverse(xform));
+                }
+                in_mesh = true;
+            } else {
+                ++ctx_n;
+                path_base = r0.z;
+                asm_inst_base = r1.y;
             }
-            in_mesh = true;
-            stack[sp++] = MARK_POP_MESH;
+            stack[sp++] = mesh ? MARK_POP_MESH : MARK_POP_ASM;
             stack[sp++] = r1.x;
-        } else if (kind == PATH_ASSEMBLY) {
-            if (ctx_n >= TRACE_MAX_NEST) return false;
-            save_ctx(ctx_n, own);
-            ++ctx_n;
-            path_base = r0.z;
-            asm_inst_base = r1.y;
-            if (own) set_local(rec_xform(S, p, xf_count, r0.y));
-            stack[sp++] = MARK_POP_ASM;
-            stack[sp++] = r1.x;
-        } else if (kind == PATH_SPHERE_LIGHT) {
-            const PsyLight l = S.lights[r1.x];
-            Xf xform = rec_xform(S, p, xf_count, r0.y);
-            V3 ol = own ? xf_point(xform, orig) : orig_local;
-            float t;
-            if (sphere_light_hit(S, l, xform, ol, dir, time, max_t, t)) {
+        } else if (kind == PATH_SPHERE_LIGHT || kind == PATH_RECT_LIGHT) {
+            const V3 ol = own ? xf_point(xform, orig) : orig_local;
+            const LightHit lh =
+                light_instance_hit(S.lights, S.light_shape, r1.x, kind, xform, orig, dir, ol, time, max_t, pre);
+            if (COUNT) cnt.tri_tests += lh.tri_tests;
+            if (lh.kind != PSY_HIT_MISS) {
                 if (occlusion) {
                     hit.kind = PSY_HIT_OCCLUDED;
                     return true;
                 }
-                max_t = t;
-                hit.kind = PSY_HIT_SPHERE_LIGHT;
-                hit.t = t;
-                hit.prim = 0;
+                max_t = lh.t;
+                hit.kind = lh.kind;
+                hit.t = lh.t;
+                hit.prim = lh.prim;
                 hit.path = p;
-                hit.b0 = hit.b1 = hit.b2 = 0.0f;
-            }
-        } else if (kind == PATH_RECT_LIGHT) {
-            const PsyLight l = S.lights[r1.x];
-            Xf xform = rec_xform(S, p, xf_count, r0.y);
-            float w, h;
-            rect_dims(S, l, time, w, h);
-            Xf space_inv = xf_inverse(xform);
-            V3 p1, p2, p3, p4;
-            rect_corners(space_inv, w, h, p1, p2, p3, p4);
-#pragma unroll 1
-            for (int k = 0; k < 2; ++k) {
-                V3 a = k == 0 ? p1 : p3, b = k == 0 ? p2 : p4, c = k == 0 ? p3 : p1;
-                float t, b0, b1, b2;
-                if (COUNT) cnt.tri_tests += 1;
-                if (tri_intersect(orig, pre, max_t, a, b, c, t, b0, b1, b2)) {
-                    if (t < max_t) {
-                        if (occlusion) {
-                            hit.kind = PSY_HIT_OCCLUDED;
-                            return true;
-                        }
-                        max_t = t;
-                        hit.kind = PSY_HIT_RECT_LIGHT;
-                        hit.t = t;
-                        hit.prim = (uint32_t)k;
-                        hit.path = p;
-                        hit.b0 = b0, hit.b1 = b1, hit.b2 = b2;
-                        break;
-                    }
-                }
+                hit.b0 = lh.b0, hit.b1 = lh.b1, hit.b2 = lh.b2;
             }
         }
         return false;
@@ -380,7 +366,7 @@ struct Traversal {
     // scene: per-lane `while(sp>0)` loops 1.9 active threads/instruction, lock-step steps without
     // parking 6.5-9.2; see profiles/.)
     // Ends when no lane has work, after `budget` iterations, or when `refill_min` lanes are idle.
-    PSY_DEV void run_warp(const DScene& S, int budget, int refill_min, int leaf_min, TraceCounters& cnt) {
+    PSY_DEV void run_warp(const DScene& S, int budget, int refill_min, int leaf_min, int inst_min, TraceCounters& cnt) {
         const uint32_t FULL = 0xffffffffu;
         for (int it = 0; it < budget; ++it) {
             const bool has_work = sp > 0 || pend != PSY_NONE;
@@ -408,12 +394,13 @@ struct Traversal {
             const bool flush_all = nm == 0u;
             if (tm && (flush_all || __popc(tm) >= leaf_min)) {
                 if (pend_tri) {
-                    bool finished = visit_triangles(S, PSY_CHILD_LEAF_START(pend), PSY_CHILD_LEAF_COUNT(pend), cnt);
-                    pend = PSY_NONE;
+                    const uint32_t start = PSY_CHILD_LEAF_START(pend), count = PSY_CHILD_LEAF_COUNT(pend);
+                    const bool finished = count != 0u && visit_triangle(S, start, cnt);
+                    pend = (count > 1u && !finished) ? PSY_CHILD_LEAF(start + 1u, count - 1u) : PSY_NONE;
                     if (finished) sp = 0;
                 }
             }
-            if (im && (flush_all || __popc(im) >= leaf_min)) {
+            if (im && (flush_all || __popc(im) >= inst_min)) {
                 if (pend_inst) {
                     bool finished = visit_instance(S, PSY_CHILD_LEAF_START(pend), cnt);
                     pend = PSY_NONE;

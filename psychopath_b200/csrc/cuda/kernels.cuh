@@ -57,7 +57,8 @@ constexpr int SHADE_CLASSES = 4;
 struct TraceTuning {
     int step_budget;  // default 24
     int refill_min;   // idle lanes that trigger a refill; 32 = classic "fetch a full warp of rays when the warp is empty"
-    int leaf_min;     // parked leaves / instance entries that trigger their joint processing
+    int leaf_min;     // parked triangle leaves that trigger their joint processing
+    int inst_min;     // parked instance entries that trigger their joint processing
 };
 
 struct ShadeQueues {
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(128, PSY_TRACE_MIN_BLOCKS) k_trace(DScene S, P
             }
         }
         if (__ballot_sync(FULL, busy) == 0u) break;
-        tr.run_warp(S, tune.step_budget, exhausted ? 33 : tune.refill_min, tune.leaf_min, cnt);
+        tr.run_warp(S, tune.step_budget, exhausted ? 33 : tune.refill_min, tune.leaf_min, tune.inst_min, cnt);
         int cls = -1;
         if (busy && tr.done()) {
             busy = false;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(128) k_trace_probe(DScene S, const PsyRay* __r
         ray.occlusion = (r.flags & PSY_RAY_OCCLUSION) != 0u;
         tr.begin(S, ray);
     }
-    tr.run_warp(S, 1 << 30, 33, 12, cnt);  // every lane of the warp takes part (lanes past n hold no ray)
+    tr.run_warp(S, 1 << 30, 33, 12, 12, cnt);  // every lane of the warp takes part (lanes past n hold no ray)
     if (i < n) {
         const HitRec h = tr.hit;
         PsyHit o;
@@ -491,3 +492,5 @@ __global__ void __launch_bounds__(128) k_film(PathPool P, Bucket b, float* out, 
 }
 
 }  // namespace psyd
+
+#include "dpool.cuh"

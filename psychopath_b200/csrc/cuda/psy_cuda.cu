@@ -79,6 +79,8 @@ struct PsyScene {
     DevBuf pool_ray_o, pool_ray_d, pool_flags, pool_sseed, pool_wl, pool_cpdf, pool_nb_o, pool_nb_d, pool_next_atten,
         pool_light_atten, pool_pending, pool_color, pool_hits, pool_light_pick, pool_light_uv, active_a, active_b;
     DevBuf counts, fetch, qcounts, queues, counters, image, bucket_out, samples_out;
+    DevBuf trace_scratch;  // k_trace_pool: child-reference stacks + saved parent spaces, [warp][level][ray]
+    uint32_t pool_trace_blocks = 0;
     size_t counts_cap = 0;
     std::vector<cudaEvent_t> events;
     size_t events_used = 0;
@@ -232,6 +234,12 @@ int32_t ensure_pool(PsyScene* sc, size_t n) {
     CK(sc->active_a.alloc(cap * 4));
     CK(sc->active_b.alloc(cap * 4));
     CK(sc->queues.alloc(cap * 4 * SHADE_CLASSES));
+    if (!sc->trace_scratch.p) {
+        sc->pool_trace_blocks = (uint32_t)sc->ctx->sm_count * PSY_POOL_MIN_BLOCKS;
+        CK(sc->trace_scratch.alloc((size_t)sc->pool_trace_blocks * POOL_WARPS * POOL_SCRATCH_WORDS_PER_WARP * 4));
+        CK(cudaFuncSetAttribute(k_trace_pool<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POOL_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_trace_pool<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POOL_SMEM_BYTES));
+    }
     sc->pool_cap = cap;
     return PSY_OK;
 }
@@ -289,18 +297,31 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
     uint32_t shade_blocks = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 16);
     ShadeQueues Q;
     static const TraceTuning tune = [] {
-        TraceTuning t{64, 12, 8};  // measured best on the C4 scene (profiles/README.md)
+        TraceTuning t{64, 12, 8, 8};  // measured best on the C4 scene (profiles/README.md)
         if (const char* e = getenv("PSY_TRACE_LEAFMIN")) t.leaf_min = atoi(e);
+        if (const char* e = getenv("PSY_TRACE_INSTMIN")) t.inst_min = atoi(e);
         if (const char* e = getenv("PSY_TRACE_BUDGET")) t.step_budget = atoi(e);
         if (const char* e = getenv("PSY_TRACE_REFILL")) t.refill_min = atoi(e);
         return t;
+    }();
+    // PSY_TRACE_KERNEL=warp selects the one-ray-per-lane kernel (k_trace) for A/B measurements
+    static const bool pool_kernel = [] {
+        const char* e = getenv("PSY_TRACE_KERNEL");
+        return !(e && std::string(e) == "warp");
     }();
     for (int c = 0; c < SHADE_CLASSES; ++c) Q.q[c] = sc->queues.as<uint32_t>() + (size_t)c * sc->pool_cap;
     uint32_t* qcounts = sc->qcounts.as<uint32_t>() + bucket_index * COUNT_SLOTS * SHADE_CLASSES;
     for (int w = 0; w < WAVES; ++w) {
         Q.count = qcounts + w * SHADE_CLASSES;
         stamp(ev ? &ev->trace : nullptr, true);
-        if (counters)
+        if (pool_kernel && counters)
+            k_trace_pool<true><<<sc->pool_trace_blocks, 32 * POOL_WARPS, POOL_SMEM_BYTES, st>>>(
+                sc->d, P, act[w & 1], counts + w, fetch + w, sc->counters.as<TraceCounters>(), Q,
+                sc->trace_scratch.as<uint32_t>());
+        else if (pool_kernel)
+            k_trace_pool<false><<<sc->pool_trace_blocks, 32 * POOL_WARPS, POOL_SMEM_BYTES, st>>>(
+                sc->d, P, act[w & 1], counts + w, fetch + w, nullptr, Q, sc->trace_scratch.as<uint32_t>());
+        else if (counters)
             k_trace<true><<<trace_blocks, 128, 0, st>>>(sc->d, P, act[w & 1], counts + w, fetch + w,
                                                         sc->counters.as<TraceCounters>(), Q, tune);
         else
@@ -653,7 +674,10 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
             }
         }
         uint32_t own = in.xform_count > 0 ? 1u : 0u;
-        path_recs[2 * i] = make_uint4(kind | (own << 3) | (dpaths[i].xf_count << 8), dpaths[i].xf_base,
+        // shading class of a triangle hit on this path (k_trace_pool files finished rays by it)
+        uint32_t sh_kind = in.shader_index == PSY_NONE ? (uint32_t)PSY_SHADER_EMIT : s->shaders[in.shader_index].kind;
+        uint32_t cls = sh_kind == PSY_SHADER_LAMBERT ? SHADE_LAMBERT : (sh_kind == PSY_SHADER_GGX ? SHADE_GGX : SHADE_EMIT);
+        path_recs[2 * i] = make_uint4(kind | (own << 3) | (cls << PREC_CLS_SHIFT) | (dpaths[i].xf_count << 8), dpaths[i].xf_base,
                                       dpaths[i].child_base, in.id);
         path_recs[2 * i + 1] = r1;
         path_static[2 * i] = paths[i].keys.size() == 1 ? psyh::to_abi(paths[i].keys[0]) : psyh::to_abi(HXf());
