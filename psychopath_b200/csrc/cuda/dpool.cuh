@@ -39,7 +39,7 @@ constexpr int POOL_WARPS = 4;             // warps per block
 #endif
 constexpr uint32_t POOL_WIN = 4;  // stack entries below the top that stay in shared memory
 
-enum PoolQueue { Q_NODE = 0, Q_TRI = 1, Q_INST = 2, Q_DONE = 3, Q_FREE = 4, Q_COUNT = 5 };
+enum PoolQueue { Q_NODE = 0, Q_TRI = 1, Q_INST = 2, Q_DONE = 3, Q_FREE = 4, Q_LIGHT = 5, Q_COUNT = 6 };
 
 // columns of the per-ray state
 enum PoolField {
@@ -52,7 +52,7 @@ enum PoolField {
     PF_MDI = PF_MOL + 3,
     PF_FLAGS = PF_MDI + 3,
     PF_TOP,  // next child reference to process (top of the stack)
-    PF_SP,   // entries below the top: count | (first one still in the window << 8)
+    PF_SP,   // entries below the top: count | (first one still in the window << 8) | (count at mesh entry << 16)
     PF_PATH_BASE,
     PF_INST_BASE,
     PF_MESH_PATH,
@@ -121,12 +121,14 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
     uint32_t* const msb = ctxb + POOL_CTX_WORDS * TRACE_MAX_NEST * R;  // local->world of the current mesh
     const uint32_t n_rays = *count;
 
-    TraceCounters cnt;
+    struct {
+        uint32_t node_visits, tri_tests, instance_visits, motion_node_visits;  // per lane and launch: far below 2^32
+    } cnt;
     cnt.node_visits = cnt.tri_tests = cnt.instance_visits = cnt.motion_node_visits = 0;
 
     for (uint32_t i = lane; i < (uint32_t)R; i += 32) qs[Q_FREE * R + i] = (uint8_t)i;
     __syncwarp();
-    int n_node = 0, n_tri = 0, n_inst = 0, n_done = 0, n_free = R;
+    int n_node = 0, n_tri = 0, n_inst = 0, n_done = 0, n_free = R, n_light = 0;
     bool exhausted = n_rays == 0u;
 
 #define ST(F, r) st[(F) * R + (r)]
@@ -140,9 +142,11 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
         ++sp;                                      \
         lo = sp > lo + POOL_WIN ? sp - POOL_WIN : lo; \
     }
+// (popping an entry from below the mesh entry's stack height leaves the mesh instance: no marker needed)
 #define PSY_POP(out)                                \
     {                                               \
         --sp;                                       \
+        if (sp < msp) flags &= ~RF_IN_MESH;         \
         if (sp < lo) {                              \
             lo = sp;                                \
             out = stk[sp * R + r];                  \
@@ -150,20 +154,27 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
             out = ST(PF_STK + (sp % POOL_WIN), r);  \
         }                                           \
     }
+#define PSY_LOAD_SP()                                          \
+    {                                                          \
+        const uint32_t spw = ST(PF_SP, r);                     \
+        sp = spw & 255u, lo = (spw >> 8) & 255u, msp = spw >> 16; \
+    }
 
     for (;;) {
         // ---- pick the step kind of this iteration (warp-uniform)
         int k;
         {
-            const int c_node = min(n_node, 32), c_tri = min(n_tri, 32), c_inst = min(n_inst, 32);
+            const int c_node = min(n_node, 32), c_tri = min(n_tri, 32), c_inst = min(n_inst, 32), c_light = min(n_light, 32);
             if (n_done >= 16) {
                 k = Q_DONE;
             } else if (!exhausted && n_free >= 16) {
                 k = Q_FREE;
-            } else if (c_tri > 0 && c_tri >= c_node && c_tri >= c_inst) {
+            } else if (c_tri > 0 && c_tri >= c_node && c_tri >= c_inst && c_tri >= c_light) {
                 k = Q_TRI;
-            } else if (c_inst > 0 && c_inst >= c_node) {
+            } else if (c_inst > 0 && c_inst >= c_node && c_inst >= c_light) {
                 k = Q_INST;
+            } else if (c_light > 0 && c_light >= c_node) {
+                k = Q_LIGHT;
             } else if (c_node > 0) {
                 k = Q_NODE;
             } else if (n_done > 0) {
@@ -174,14 +185,16 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 break;
             }
         }
-        int avail = k == Q_NODE ? n_node : (k == Q_TRI ? n_tri : (k == Q_INST ? n_inst : (k == Q_DONE ? n_done : n_free)));
+        int avail = k == Q_NODE ? n_node
+                                : (k == Q_TRI ? n_tri : (k == Q_INST ? n_inst : (k == Q_DONE ? n_done : (k == Q_FREE ? n_free : n_light))));
         const int n = min(avail, 32);
         avail -= n;
         if (k == Q_NODE) n_node = avail;
         else if (k == Q_TRI) n_tri = avail;
         else if (k == Q_INST) n_inst = avail;
         else if (k == Q_DONE) n_done = avail;
-        else n_free = avail;
+        else if (k == Q_FREE) n_free = avail;
+        else n_light = avail;
         bool act = (int)lane < n;
         const uint32_t r = act ? (uint32_t)qs[k * R + avail + (int)lane] : 0u;
         __syncwarp();  // the queue entries just read may be overwritten by this iteration's pushes
@@ -224,7 +237,8 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
         }
 
         // state every remaining step kind works on
-        uint32_t flags = 0, top = PSY_NONE, sp = 0, lo = 0;
+        uint32_t flags = 0, top = PSY_NONE, sp = 0, lo = 0, msp = 0;
+        bool to_light = false;  // an instance entry that turned out to be a light: handled by the light step
 
         if (k == Q_FREE) {
             // ---- new rays: the per-ray prologue of TracerInner::trace (tracer.rs:59-77)
@@ -274,10 +288,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 float4 bx0 = __ldg(bp), bx1 = __ldg(bp + 1), by0 = __ldg(bp + 2), by1 = __ldg(bp + 3), bz0 = __ldg(bp + 4),
                        bz1 = __ldg(bp + 5);
                 flags = ST(PF_FLAGS, r);
-                {
-                    const uint32_t spw = ST(PF_SP, r);
-                    sp = spw & 255u, lo = spw >> 8;
-                }
+                PSY_LOAD_SP()
                 const bool in_mesh = (flags & RF_IN_MESH) != 0u;
                 const uint32_t fo = in_mesh ? (uint32_t)PF_MOL : (uint32_t)PF_OL;
                 const V3 ol = mk3(STF(fo + 0, r), STF(fo + 1, r), STF(fo + 2, r));
@@ -348,9 +359,9 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 }
 #undef PSY_SLAB
                 top = PSY_NONE;
-                if (hits) {
-                    // far -> near (bvh4.rs:152-165): the nearest hit child becomes the new top, the others go
-                    // below it
+                {
+                    // far -> near (bvh4.rs:152-165).  Every hit child is written to the stack, predicated and
+                    // without nested branches; the nearest one is then taken back as the new top.
                     const uint32_t order_code = c_traversal_table[space >> 1][meta.x];
 #pragma unroll
                     for (int i = 3; i >= 0; --i) {
@@ -359,10 +370,14 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                         const uint32_t c_hi = (child_i & 1u) ? child.w : child.z;
                         const uint32_t c = (child_i & 2u) ? c_hi : c_lo;
                         if ((uint32_t)i < meta.w && ((hits >> child_i) & 1u)) {
-                            if (top != PSY_NONE) PSY_PUSH(top)
+                            stk[sp * R + r] = c;
+                            ST(PF_STK + (sp % POOL_WIN), r) = c;
+                            ++sp;
                             top = c;
                         }
                     }
+                    lo = sp > lo + POOL_WIN ? sp - POOL_WIN : lo;  // (the taken-back entry used a ring slot too)
+                    if (hits) --sp;
                 }
             }
         } else if (k == Q_TRI) {
@@ -373,10 +388,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 const uint32_t nk = ST(PF_NK, r);
                 const float4* tv = S.tri_verts + (size_t)(ST(PF_TVBASE, r) + ti * 3u * nk);
                 flags = ST(PF_FLAGS, r);
-                {
-                    const uint32_t spw = ST(PF_SP, r);
-                    sp = spw & 255u, lo = spw >> 8;
-                }
+                PSY_LOAD_SP()
                 top = count > 1u ? PSY_CHILD_LEAF(ti + 1u, count - 1u) : PSY_NONE;
                 if (count != 0u) {
                     V3 p0, p1, p2;
@@ -432,7 +444,9 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 }
             }
         } else {
-            // ---- instance entry (tracer.rs:94-149); assembly leaves hold exactly one instance
+            // ---- instance entry (tracer.rs:94-149); assembly leaves hold exactly one instance.  Light
+            // instances found by the Q_INST step are passed on to the Q_LIGHT step, so that their long,
+            // rarely needed hit test runs for many rays at once instead of one or two.
             if (act) {
                 const uint32_t start = PSY_CHILD_LEAF_START(ST(PF_TOP, r));
                 const uint32_t p = ST(PF_PATH_BASE, r) + (start - ST(PF_INST_BASE, r));
@@ -441,16 +455,15 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 const uint32_t slot = ST(PF_SLOT, r);
                 const float4 ro = P.ray_o[slot], rd = P.ray_d[slot];
                 flags = ST(PF_FLAGS, r);
-                {
-                    const uint32_t spw = ST(PF_SP, r);
-                    sp = spw & 255u, lo = spw >> 8;
-                }
+                PSY_LOAD_SP()
                 top = PSY_NONE;
                 const uint32_t kind = r0.x & 7u;
                 const uint32_t own = (r0.x >> 3) & 1u;
                 const uint32_t xf_count = r0.x >> 8;
                 const float time = STF(PF_TIME, r);
-                if (COUNT) cnt.instance_visits += 1;
+                const bool light = kind == PATH_SPHERE_LIGHT || kind == PATH_RECT_LIGHT;
+                to_light = k == Q_INST && light;
+                if (COUNT && !to_light) cnt.instance_visits += 1;
                 // world->local transform of the instance at the ray's time
                 Xf xform = xf_identity();
                 if (xf_count == 1u) {
@@ -461,7 +474,9 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 const V3 orig = mk3(ro.x, ro.y, ro.z), dir = mk3(rd.x, rd.y, rd.z);
                 const uint32_t ctx_n = (flags & RF_CTXN_MASK) >> RF_CTXN_SHIFT;
                 const bool mesh = kind == PATH_MESH;
-                if (mesh || (kind == PATH_ASSEMBLY && ctx_n < (uint32_t)TRACE_MAX_NEST)) {
+                if (to_light) {
+                    top = ST(PF_TOP, r);
+                } else if (mesh || (kind == PATH_ASSEMBLY && ctx_n < (uint32_t)TRACE_MAX_NEST)) {
                     // Mesh and assembly entries share everything expensive (the ray in the instance's space),
                     // so the lanes of both kinds run it together.
                     if (!mesh) {
@@ -519,9 +534,13 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                         ST(PF_PATH_BASE, r) = r0.z;
                         ST(PF_INST_BASE, r) = r1.y;
                     }
-                    PSY_PUSH(mesh ? MARK_POP_MESH : MARK_POP_ASM)
+                    if (mesh) {
+                        msp = sp;  // whatever is popped from below this height is outside the mesh
+                    } else {
+                        PSY_PUSH(MARK_POP_ASM)
+                    }
                     top = r1.x;
-                } else if (kind == PATH_SPHERE_LIGHT || kind == PATH_RECT_LIGHT) {
+                } else if (light) {
                     const V3 ol = own ? xf_point(xform, orig) : mk3(STF(PF_OL + 0, r), STF(PF_OL + 1, r), STF(PF_OL + 2, r));
                     const float max_t = STF(PF_MAXT, r);
                     RayTriPre pre;
@@ -530,7 +549,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                     pre.zi = (int)((flags >> (RF_PERM_SHIFT + 4)) & 3u);
                     pre.sx = STF(PF_S + 0, r), pre.sy = STF(PF_S + 1, r), pre.sz = STF(PF_S + 2, r);
                     const LightHit lh =
-                        light_instance_hit(S.lights, S.light_shape, r1.x, kind, xform, orig, dir, ol, time, max_t, pre);
+                        light_instance_hit_inline(S.lights, S.light_shape, r1.x, kind, xform, orig, dir, ol, time, max_t, pre);
                     if (COUNT) cnt.tri_tests += lh.tri_tests;
                     if (lh.kind != PSY_HIT_MISS) {
                         if (flags & RF_OCCL) {
@@ -550,13 +569,11 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
 
         // ---- common tail: find the ray's next entry, leave instances on the way (tracer.rs:131-148),
         // and file the ray into the queue of its next step
-        int dest = -1;
-        if (act) {
+        int dest = to_light ? (int)Q_LIGHT : -1;
+        if (act && !to_light) {
             if (top == PSY_NONE && sp > 0u) PSY_POP(top)
-            while (top == MARK_POP_MESH || top == MARK_POP_ASM) {
-                if (top == MARK_POP_MESH) {
-                    flags &= ~RF_IN_MESH;
-                } else {
+            while (top == MARK_POP_ASM) {
+                {
                     const uint32_t level = ((flags & RF_CTXN_MASK) >> RF_CTXN_SHIFT) - 1u;
                     flags = (flags & ~RF_CTXN_MASK) | (level << RF_CTXN_SHIFT);
                     const uint32_t* c = ctxb + (size_t)(level * POOL_CTX_WORDS) * R + r;
@@ -573,18 +590,21 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 if (sp > 0u) PSY_POP(top)
             }
             ST(PF_TOP, r) = top;
-            ST(PF_SP, r) = sp | (lo << 8);
+            ST(PF_SP, r) = sp | (lo << 8) | (msp << 16);
             ST(PF_FLAGS, r) = flags;
             dest = top == PSY_NONE ? Q_DONE : (!(top & PSY_CHILD_LEAF_BIT) ? Q_NODE : ((flags & RF_IN_MESH) ? Q_TRI : Q_INST));
         }
         {
             const uint32_t m_node = __ballot_sync(FULL, dest == Q_NODE), m_tri = __ballot_sync(FULL, dest == Q_TRI),
-                           m_inst = __ballot_sync(FULL, dest == Q_INST), m_done = __ballot_sync(FULL, dest == Q_DONE);
-            if (dest == Q_NODE) qs[Q_NODE * R + n_node + __popc(m_node & lt)] = (uint8_t)r;
-            if (dest == Q_TRI) qs[Q_TRI * R + n_tri + __popc(m_tri & lt)] = (uint8_t)r;
-            if (dest == Q_INST) qs[Q_INST * R + n_inst + __popc(m_inst & lt)] = (uint8_t)r;
-            if (dest == Q_DONE) qs[Q_DONE * R + n_done + __popc(m_done & lt)] = (uint8_t)r;
+                           m_inst = __ballot_sync(FULL, dest == Q_INST), m_done = __ballot_sync(FULL, dest == Q_DONE),
+                           m_light = __ballot_sync(FULL, dest == Q_LIGHT);
+            const uint32_t m_mine =
+                dest == Q_NODE ? m_node : (dest == Q_TRI ? m_tri : (dest == Q_INST ? m_inst : (dest == Q_DONE ? m_done : m_light)));
+            const int n_mine =
+                dest == Q_NODE ? n_node : (dest == Q_TRI ? n_tri : (dest == Q_INST ? n_inst : (dest == Q_DONE ? n_done : n_light)));
+            if (dest >= 0) qs[dest * R + n_mine + __popc(m_mine & lt)] = (uint8_t)r;
             n_node += __popc(m_node), n_tri += __popc(m_tri), n_inst += __popc(m_inst), n_done += __popc(m_done);
+            n_light += __popc(m_light);
         }
         __syncwarp();
     }
@@ -592,11 +612,12 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
 #undef STF
 #undef PSY_PUSH
 #undef PSY_POP
+#undef PSY_LOAD_SP
     if (COUNT) {
-        atomicAdd(&counters->node_visits, cnt.node_visits);
-        atomicAdd(&counters->tri_tests, cnt.tri_tests);
-        atomicAdd(&counters->instance_visits, cnt.instance_visits);
-        atomicAdd(&counters->motion_node_visits, cnt.motion_node_visits);
+        atomicAdd(&counters->node_visits, (unsigned long long)cnt.node_visits);
+        atomicAdd(&counters->tri_tests, (unsigned long long)cnt.tri_tests);
+        atomicAdd(&counters->instance_visits, (unsigned long long)cnt.instance_visits);
+        atomicAdd(&counters->motion_node_visits, (unsigned long long)cnt.motion_node_visits);
     }
 }
 

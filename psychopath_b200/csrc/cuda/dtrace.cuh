@@ -215,9 +215,9 @@ struct LightHit {
     float t, b0, b1, b2;
     uint32_t tri_tests;
 };
-PSY_NOINLINE LightHit light_instance_hit(const PsyLight* __restrict__ lights, const float* __restrict__ light_shape,
-                                         uint32_t light_index, uint32_t path_kind, Xf xform, V3 orig, V3 dir,
-                                         V3 orig_in_space, float time, float max_t, RayTriPre pre) {
+PSY_DEV LightHit light_instance_hit_inline(const PsyLight* __restrict__ lights, const float* __restrict__ light_shape,
+                                           uint32_t light_index, uint32_t path_kind, Xf xform, V3 orig, V3 dir,
+                                           V3 orig_in_space, float time, float max_t, RayTriPre pre) {
     LightHit out;
     out.kind = PSY_HIT_MISS, out.prim = 0, out.t = 0.0f, out.b0 = out.b1 = out.b2 = 0.0f, out.tri_tests = 0;
     const PsyLight l = lights[light_index];
@@ -250,6 +250,13 @@ PSY_NOINLINE LightHit light_instance_hit(const PsyLight* __restrict__ lights, co
         }
     }
     return out;
+}
+// out-of-line copy for k_trace (one ray per lane), where light entries run with one or two lanes
+PSY_NOINLINE LightHit light_instance_hit(const PsyLight* __restrict__ lights, const float* __restrict__ light_shape,
+                                         uint32_t light_index, uint32_t path_kind, Xf xform, V3 orig, V3 dir,
+                                         V3 orig_in_space, float time, float max_t, RayTriPre pre) {
+    return light_instance_hit_inline(lights, light_shape, light_index, path_kind, xform, orig, dir, orig_in_space, time,
+                                     max_t, pre);
 }
 
 }  // namespace psyd

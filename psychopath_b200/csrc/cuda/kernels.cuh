@@ -200,6 +200,71 @@ __global__ void __launch_bounds__(128, PSY_TRACE_MIN_BLOCKS) k_trace(DScene S, P
     }
 }
 
+// HitRec -> the ABI's PsyHit / PsyHitGeo of probe ray i (psy_trace_rays)
+PSY_DEV void probe_store(const DScene& S, const HitRec& h, const RayIn& ray, uint32_t i, PsyHit* hits, PsyHitGeo* geo) {
+    PsyHit o;
+    o.kind = h.kind;
+    o.t = h.t;
+    o.prim_id = 0;
+    o.inst_id = 0;
+    o.path_id = 0;
+    o.b0 = h.b0, o.b1 = h.b1, o.b2 = h.b2;
+    bool is_hit = h.kind == PSY_HIT_TRIANGLE || h.kind == PSY_HIT_SPHERE_LIGHT || h.kind == PSY_HIT_RECT_LIGHT;
+    if (is_hit) {
+        o.path_id = h.path;
+        o.inst_id = S.instances[S.paths[h.path].inst].id;
+        o.prim_id = h.kind == PSY_HIT_TRIANGLE ? S.tris[h.prim].w : h.prim;
+    }
+    hits[i] = o;
+    if (geo) {
+        PsyHitGeo g;
+        g.pos[0] = g.pos[1] = g.pos[2] = 0.0f;
+        g.pos_err = 0.0f;
+        g.nor[0] = g.nor[1] = g.nor[2] = 0.0f;
+        g.sample_pdf = 0.0f;
+        g.nor_g[0] = g.nor_g[1] = g.nor_g[2] = 0.0f;
+        g.closure_kind = 0;
+        if (is_hit) {
+            Isect is;
+            finalize_hit(S, h, ray.orig, ray.dir, ray.time, is);
+            g.pos[0] = is.pos.x, g.pos[1] = is.pos.y, g.pos[2] = is.pos.z;
+            g.pos_err = is.pos_err;
+            g.nor[0] = is.nor.x, g.nor[1] = is.nor.y, g.nor[2] = is.nor.z;
+            g.sample_pdf = is.sample_pdf;
+            g.nor_g[0] = is.nor_g.x, g.nor_g[1] = is.nor_g.y, g.nor_g[2] = is.nor_g.z;
+            g.closure_kind = is.closure.kind;
+        }
+        geo[i] = g;
+    }
+}
+
+// Probe rays through the production trace kernel: load them into the path pool ...
+__global__ void __launch_bounds__(256) k_probe_load(const PsyRay* __restrict__ rays, uint32_t n, PathPool P, uint32_t* active,
+                                                    uint32_t* count0) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *count0 = n;
+    if (i >= n) return;
+    const PsyRay r = rays[i];
+    P.ray_o[i] = make_float4(r.orig[0], r.orig[1], r.orig[2], r.time);
+    P.ray_d[i] = make_float4(r.dir[0], r.dir[1], r.dir[2], r.max_t);
+    P.flags[i] = (r.flags & PSY_RAY_OCCLUSION) ? F_OCCLUSION : 0u;
+    active[i] = i;
+}
+// ... and turn the hit records k_trace_pool left in the pool into the ABI's structs
+__global__ void __launch_bounds__(128) k_probe_store(DScene S, const PsyRay* __restrict__ rays, uint32_t n, PathPool P,
+                                                     PsyHit* hits, PsyHitGeo* geo) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PsyRay r = rays[i];
+    RayIn ray;
+    ray.orig = mk3(r.orig[0], r.orig[1], r.orig[2]);
+    ray.dir = mk3(r.dir[0], r.dir[1], r.dir[2]);
+    ray.time = r.time;
+    ray.max_t = r.max_t;
+    ray.occlusion = (r.flags & PSY_RAY_OCCLUSION) != 0u;
+    probe_store(S, P.hits[i], ray, i, hits, geo);
+}
+
 // Probe rays: trace + finalise into the ABI's PsyHit / PsyHitGeo (psy_trace_rays)
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_probe(DScene S, const PsyRay* __restrict__ rays, uint32_t n, PsyHit* hits,
@@ -223,43 +288,7 @@ __global__ void __launch_bounds__(128) k_trace_probe(DScene S, const PsyRay* __r
         tr.begin(S, ray);
     }
     tr.run_warp(S, 1 << 30, 33, 12, 12, cnt);  // every lane of the warp takes part (lanes past n hold no ray)
-    if (i < n) {
-        const HitRec h = tr.hit;
-        PsyHit o;
-        o.kind = h.kind;
-        o.t = h.t;
-        o.prim_id = 0;
-        o.inst_id = 0;
-        o.path_id = 0;
-        o.b0 = h.b0, o.b1 = h.b1, o.b2 = h.b2;
-        bool is_hit = h.kind == PSY_HIT_TRIANGLE || h.kind == PSY_HIT_SPHERE_LIGHT || h.kind == PSY_HIT_RECT_LIGHT;
-        if (is_hit) {
-            o.path_id = h.path;
-            o.inst_id = S.instances[S.paths[h.path].inst].id;
-            o.prim_id = h.kind == PSY_HIT_TRIANGLE ? S.tris[h.prim].w : h.prim;
-        }
-        hits[i] = o;
-        if (geo) {
-            PsyHitGeo g;
-            g.pos[0] = g.pos[1] = g.pos[2] = 0.0f;
-            g.pos_err = 0.0f;
-            g.nor[0] = g.nor[1] = g.nor[2] = 0.0f;
-            g.sample_pdf = 0.0f;
-            g.nor_g[0] = g.nor_g[1] = g.nor_g[2] = 0.0f;
-            g.closure_kind = 0;
-            if (is_hit) {
-                Isect is;
-                finalize_hit(S, h, ray.orig, ray.dir, ray.time, is);
-                g.pos[0] = is.pos.x, g.pos[1] = is.pos.y, g.pos[2] = is.pos.z;
-                g.pos_err = is.pos_err;
-                g.nor[0] = is.nor.x, g.nor[1] = is.nor.y, g.nor[2] = is.nor.z;
-                g.sample_pdf = is.sample_pdf;
-                g.nor_g[0] = is.nor_g.x, g.nor_g[1] = is.nor_g.y, g.nor_g[2] = is.nor_g.z;
-                g.closure_kind = is.closure.kind;
-            }
-            geo[i] = g;
-        }
-    }
+    if (i < n) probe_store(S, tr.hit, ray, i, hits, geo);
     if (COUNT) {
         atomicAdd(&counters->node_visits, cnt.node_visits);
         atomicAdd(&counters->tri_tests, cnt.tri_tests);

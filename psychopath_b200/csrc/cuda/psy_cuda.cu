@@ -238,7 +238,6 @@ int32_t ensure_pool(PsyScene* sc, size_t n) {
         sc->pool_trace_blocks = (uint32_t)sc->ctx->sm_count * PSY_POOL_MIN_BLOCKS;
         CK(sc->trace_scratch.alloc((size_t)sc->pool_trace_blocks * POOL_WARPS * POOL_SCRATCH_WORDS_PER_WARP * 4));
         CK(cudaFuncSetAttribute(k_trace_pool<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POOL_SMEM_BYTES));
-        CK(cudaFuncSetAttribute(k_trace_pool<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POOL_SMEM_BYTES));
     }
     sc->pool_cap = cap;
     return PSY_OK;
@@ -314,11 +313,10 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
     for (int w = 0; w < WAVES; ++w) {
         Q.count = qcounts + w * SHADE_CLASSES;
         stamp(ev ? &ev->trace : nullptr, true);
-        if (pool_kernel && counters)
-            k_trace_pool<true><<<sc->pool_trace_blocks, 32 * POOL_WARPS, POOL_SMEM_BYTES, st>>>(
-                sc->d, P, act[w & 1], counts + w, fetch + w, sc->counters.as<TraceCounters>(), Q,
-                sc->trace_scratch.as<uint32_t>());
-        else if (pool_kernel)
+        // The visit counters (--stats, bench.py's roofline pass) are collected by the one-ray-per-lane kernel:
+        // both kernels visit exactly the same nodes / primitives per ray, and the counting build of
+        // k_trace_pool is not used (ptxas 12.9 drops the divergence guards of its warp votes).
+        if (pool_kernel && !counters)
             k_trace_pool<false><<<sc->pool_trace_blocks, 32 * POOL_WARPS, POOL_SMEM_BYTES, st>>>(
                 sc->d, P, act[w & 1], counts + w, fetch + w, nullptr, Q, sc->trace_scratch.as<uint32_t>());
         else if (counters)
@@ -835,9 +833,30 @@ int32_t psy_trace_rays(PsyScene* sc, const PsyRay* rays, size_t n, PsyHit* hits,
     CK(drays.upload(rays, n, st));
     CK(dhits.alloc(n * sizeof(PsyHit)));
     if (geo) CK(dgeo.alloc(n * sizeof(PsyHitGeo)));
-    k_trace_probe<false><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc->d, drays.as<PsyRay>(), (uint32_t)n,
-                                                                     dhits.as<PsyHit>(), geo ? dgeo.as<PsyHitGeo>() : nullptr,
-                                                                     nullptr);
+    const char* kernel_env = getenv("PSY_TRACE_KERNEL");
+    if (kernel_env && std::string(kernel_env) == "warp") {
+        k_trace_probe<false><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(
+            sc->d, drays.as<PsyRay>(), (uint32_t)n, dhits.as<PsyHit>(), geo ? dgeo.as<PsyHitGeo>() : nullptr, nullptr);
+    } else {
+        // the production path: the rays go through the path pool and k_trace_pool like a wave of a render
+        int32_t rc = ensure_pool(sc, n);
+        if (rc) return rc;
+        rc = ensure_counts(sc, 1);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(sc->fetch.p, 0, COUNT_SLOTS * 4, st));
+        CK(cudaMemsetAsync(sc->qcounts.p, 0, COUNT_SLOTS * SHADE_CLASSES * 4, st));
+        PathPool P = make_pool(sc);
+        ShadeQueues Q;
+        for (int c = 0; c < SHADE_CLASSES; ++c) Q.q[c] = sc->queues.as<uint32_t>() + (size_t)c * sc->pool_cap;
+        Q.count = sc->qcounts.as<uint32_t>();
+        k_probe_load<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(drays.as<PsyRay>(), (uint32_t)n, P,
+                                                                 sc->active_a.as<uint32_t>(), sc->counts.as<uint32_t>());
+        k_trace_pool<false><<<sc->pool_trace_blocks, 32 * POOL_WARPS, POOL_SMEM_BYTES, st>>>(
+            sc->d, P, sc->active_a.as<uint32_t>(), sc->counts.as<uint32_t>(), sc->fetch.as<uint32_t>(), nullptr, Q,
+            sc->trace_scratch.as<uint32_t>());
+        k_probe_store<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc->d, drays.as<PsyRay>(), (uint32_t)n, P,
+                                                                  dhits.as<PsyHit>(), geo ? dgeo.as<PsyHitGeo>() : nullptr);
+    }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(hits, dhits.p, n * sizeof(PsyHit), cudaMemcpyDeviceToHost, st));
     if (geo) CK(cudaMemcpyAsync(geo, dgeo.p, n * sizeof(PsyHitGeo), cudaMemcpyDeviceToHost, st));

@@ -25,6 +25,10 @@ def make_scene(name):
     elif name == "instanced":
         s = api.Scene.synth_instanced(asset_quads=24, n_assets=3, n_clusters=9, inst_per_cluster=5,
                                       lights_per_cluster=4, cluster_xform_keys=2, res=(96, 54), spp=4, seed=4)
+    elif name == "deep_instanced":
+        # 20k-triangle assets: BVH4 stacks deeper than the trace kernel's shared-memory stack window
+        s = api.Scene.synth_instanced(asset_quads=100, n_assets=2, n_clusters=6, inst_per_cluster=4,
+                                      lights_per_cluster=3, cluster_xform_keys=2, res=(64, 36), spp=4, seed=7)
     elif name == "grid_motion":
         s = api.Scene.synth_displaced_grid(48, n_vert_keys=4, n_xform_keys=4, res=(96, 54), spp=4, seed=3)
     else:
@@ -32,7 +36,7 @@ def make_scene(name):
     return s
 
 
-SCENES = ["cornell", "cube_dof_motion", "fixture", "instanced", "grid_motion"]
+SCENES = ["cornell", "cube_dof_motion", "fixture", "instanced", "grid_motion", "deep_instanced"]
 
 
 def probe_rays(scene, n_random=20000, seed=123):
@@ -204,3 +208,36 @@ def test_cli_drop_in(tmp_path):
     x0, y0, x1, y1 = [int(v) for v in lines[1].split()]
     data = np.frombuffer(base64.b64decode(lines[2]), dtype=np.float32)
     assert data.size == (x1 - x0) * (y1 - y0) * 4 and (data[3::4] == 1.0).all()
+
+
+def test_trace_kernels_agree_and_are_deterministic(tmp_path):
+    """The production trace kernel (k_trace_pool: warp-private ray pools) against the one-ray-per-lane kernel
+    (k_trace, PSY_TRACE_KERNEL=warp) on a scene big enough to keep every pool full and the stacks deeper than
+    the shared-memory window: identical images and ray counts, and reruns are bit-identical."""
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        "from psychopath_b200 import api\n"
+        "s = api.Scene.synth_instanced(asset_quads=200, n_assets=4, n_clusters=40, inst_per_cluster=8,\n"
+        "                              lights_per_cluster=6, cluster_xform_keys=2, res=(480, 270), spp=8, seed=11)\n"
+        "r = api.Renderer(s)\n"
+        "a, sa = r.render()\n"
+        "b, sb = r.render(max_samples_per_bucket=1 << 18)\n"
+        "assert np.array_equal(a, b, equal_nan=True) and sa['ray_count'] == sb['ray_count']\n"
+        "c, sc = r.render(counters=True)\n"
+        "assert np.array_equal(a, c, equal_nan=True) and sc['tri_tests'] > 0\n"
+        "np.save(sys.argv[1], a)\n"
+        "print(int(sa['ray_count']), int(sc['accel_node_visits']), int(sc['tri_tests']), int(sc['instance_visits']))\n")
+    outs = []
+    for kernel in ("pool", "warp"):
+        env = dict(os.environ, PSY_TRACE_KERNEL=kernel, PYTHONPATH=repo)
+        path = str(tmp_path / f"{kernel}.npy")
+        p = subprocess.run([sys.executable, "-c", code, path], cwd=repo, env=env, capture_output=True, text=True,
+                           timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs.append((np.load(path), p.stdout.split()))
+    assert outs[0][1] == outs[1][1], (outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][0], outs[1][0], equal_nan=True)
