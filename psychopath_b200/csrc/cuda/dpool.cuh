@@ -128,8 +128,11 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
 
     for (uint32_t i = lane; i < (uint32_t)R; i += 32) qs[Q_FREE * R + i] = (uint8_t)i;
     __syncwarp();
-    int n_node = 0, n_tri = 0, n_inst = 0, n_done = 0, n_free = R, n_light = 0;
+    // The queues are LIFO arrays of R bytes; their lengths are packed 8 bits per queue into one warp-uniform
+    // 64-bit register, so "the length of queue k" is a shift, not a select chain.
+    uint64_t qn = (uint64_t)R << (8 * Q_FREE);
     bool exhausted = n_rays == 0u;
+#define QLEN(k) ((uint32_t)(qn >> (8 * (k))) & 255u)
 
 #define ST(F, r) st[(F) * R + (r)]
 #define STF(F, r) __uint_as_float(st[(F) * R + (r)])
@@ -162,41 +165,32 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
 
     for (;;) {
         // ---- pick the step kind of this iteration (warp-uniform)
-        int k;
+        // Finished rays and free slots are recycled as soon as half a warp of them has gathered; otherwise the
+        // fullest of the four work queues runs (ties: triangle > instance > light > node).
+        uint32_t k;
         {
-            const int c_node = min(n_node, 32), c_tri = min(n_tri, 32), c_inst = min(n_inst, 32), c_light = min(n_light, 32);
-            if (n_done >= 16) {
+            const uint32_t n_done = QLEN(Q_DONE), n_free = QLEN(Q_FREE);
+            const uint32_t key_node = min(QLEN(Q_NODE), 32u) * 8u + 0u, key_light = min(QLEN(Q_LIGHT), 32u) * 8u + 1u,
+                           key_inst = min(QLEN(Q_INST), 32u) * 8u + 2u, key_tri = min(QLEN(Q_TRI), 32u) * 8u + 3u;
+            const uint32_t best = max(max(key_node, key_light), max(key_inst, key_tri));
+            if (n_done >= 16u) {
                 k = Q_DONE;
-            } else if (!exhausted && n_free >= 16) {
+            } else if (!exhausted && n_free >= 16u) {
                 k = Q_FREE;
-            } else if (c_tri > 0 && c_tri >= c_node && c_tri >= c_inst && c_tri >= c_light) {
-                k = Q_TRI;
-            } else if (c_inst > 0 && c_inst >= c_node && c_inst >= c_light) {
-                k = Q_INST;
-            } else if (c_light > 0 && c_light >= c_node) {
-                k = Q_LIGHT;
-            } else if (c_node > 0) {
-                k = Q_NODE;
-            } else if (n_done > 0) {
+            } else if (best >= 8u) {
+                k = (0x1250u >> ((best & 7u) * 4u)) & 15u;  // tie-break rank -> queue: 0 node, 1 light, 2 inst, 3 tri
+            } else if (n_done > 0u) {
                 k = Q_DONE;
-            } else if (!exhausted && n_free > 0) {
+            } else if (!exhausted && n_free > 0u) {
                 k = Q_FREE;
             } else {
                 break;
             }
         }
-        int avail = k == Q_NODE ? n_node
-                                : (k == Q_TRI ? n_tri : (k == Q_INST ? n_inst : (k == Q_DONE ? n_done : (k == Q_FREE ? n_free : n_light))));
-        const int n = min(avail, 32);
-        avail -= n;
-        if (k == Q_NODE) n_node = avail;
-        else if (k == Q_TRI) n_tri = avail;
-        else if (k == Q_INST) n_inst = avail;
-        else if (k == Q_DONE) n_done = avail;
-        else if (k == Q_FREE) n_free = avail;
-        else n_light = avail;
-        bool act = (int)lane < n;
-        const uint32_t r = act ? (uint32_t)qs[k * R + avail + (int)lane] : 0u;
+        const uint32_t n = min(QLEN(k), 32u);
+        bool act = lane < n;
+        qn -= (uint64_t)n << (8u * k);
+        const uint32_t r = act ? (uint32_t)qs[k * R + QLEN(k) + lane] : 0u;
         __syncwarp();  // the queue entries just read may be overwritten by this iteration's pushes
 
         // ---- finished rays: hit record, shading class, slot back to the free list
@@ -219,9 +213,9 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 } else {
                     cls = (int)((flags >> RF_HCLS_SHIFT) & 3u);
                 }
-                qs[Q_FREE * R + n_free + (int)lane] = (uint8_t)r;
+                qs[Q_FREE * R + QLEN(Q_FREE) + lane] = (uint8_t)r;
             }
-            n_free += n;
+            qn += (uint64_t)n << (8 * Q_FREE);
 #pragma unroll
             for (int c = 0; c < SHADE_CLASSES; ++c) {
                 const uint32_t mask = __ballot_sync(FULL, cls == c);
@@ -248,8 +242,8 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
             if (base + (uint32_t)n >= n_rays) exhausted = true;
             const bool got = act && base + lane < n_rays;
             const uint32_t back = __ballot_sync(FULL, act && !got);
-            if (act && !got) qs[Q_FREE * R + n_free + __popc(back & lt)] = (uint8_t)r;
-            n_free += __popc(back);
+            if (act && !got) qs[Q_FREE * R + QLEN(Q_FREE) + __popc(back & lt)] = (uint8_t)r;
+            qn += (uint64_t)__popc(back) << (8 * Q_FREE);
             act = got;
             if (act) {
                 const uint32_t slot = active[base + lane];
@@ -595,19 +589,18 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
             dest = top == PSY_NONE ? Q_DONE : (!(top & PSY_CHILD_LEAF_BIT) ? Q_NODE : ((flags & RF_IN_MESH) ? Q_TRI : Q_INST));
         }
         {
-            const uint32_t m_node = __ballot_sync(FULL, dest == Q_NODE), m_tri = __ballot_sync(FULL, dest == Q_TRI),
-                           m_inst = __ballot_sync(FULL, dest == Q_INST), m_done = __ballot_sync(FULL, dest == Q_DONE),
-                           m_light = __ballot_sync(FULL, dest == Q_LIGHT);
-            const uint32_t m_mine =
-                dest == Q_NODE ? m_node : (dest == Q_TRI ? m_tri : (dest == Q_INST ? m_inst : (dest == Q_DONE ? m_done : m_light)));
-            const int n_mine =
-                dest == Q_NODE ? n_node : (dest == Q_TRI ? n_tri : (dest == Q_INST ? n_inst : (dest == Q_DONE ? n_done : n_light)));
-            if (dest >= 0) qs[dest * R + n_mine + __popc(m_mine & lt)] = (uint8_t)r;
-            n_node += __popc(m_node), n_tri += __popc(m_tri), n_inst += __popc(m_inst), n_done += __popc(m_done);
-            n_light += __popc(m_light);
+            // lanes filing into the same queue find each other with one match; the new lengths are two warp sums
+            const uint32_t m_mine = __match_any_sync(FULL, dest);
+            // (FIFO queues + prefetch.global.L1/.L2 of the filed ray's next node were tried: no gain, r1 log in
+            // profiles/README.md; the queues stay LIFO, which keeps a ray's nodes warm in L1.)
+            if (dest >= 0) qs[(uint32_t)dest * R + QLEN((uint32_t)dest) + __popc(m_mine & lt)] = (uint8_t)r;
+            const uint32_t add_lo = __reduce_add_sync(FULL, (dest >= 0 && dest < 4) ? 1u << (8 * dest) : 0u);
+            const uint32_t add_hi = __reduce_add_sync(FULL, dest == Q_LIGHT ? 1u << (8 * (Q_LIGHT - 4)) : 0u);
+            qn += (uint64_t)add_lo | ((uint64_t)add_hi << 32);
         }
         __syncwarp();
     }
+#undef QLEN
 #undef ST
 #undef STF
 #undef PSY_PUSH

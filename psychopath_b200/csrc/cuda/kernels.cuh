@@ -39,6 +39,8 @@ struct PathPool {
     HitRec* hits;
     uint4* light_pick;  // k_shade_select -> k_shade: LightPick (kind, index, parent path, selection pdf)
     float2* light_uv;   // the two light-sampling random numbers of the same Sobol vector
+    float4* sh_o;       // k_shade_light -> k_shade: shadow ray origin, w = 1 when a light sample was found
+    float4* sh_d;       // shadow ray direction, w = max_t
 };
 
 struct Bucket {
@@ -351,100 +353,195 @@ PSY_DEV bool path_next(const DScene& S, const PathPool& P, uint32_t slot, const 
         P.color[slot] = to_f4(col);
         return false;
     }
-    constexpr uint32_t KIND = CLS == SHADE_LAMBERT ? (uint32_t)PSY_SHADER_LAMBERT : (uint32_t)PSY_SHADER_GGX;
-    light_attenuation = light_attenuation / closure_sample_pdf;
-    const ShadeCtx shade_ctx = closure_prepare<KIND>(S, is.closure, dir, is.nor, is.nor_g, wl);
-
-    // light sample (renderer.rs:488-596)
-    uint32_t sseed = P.sseed[slot];
-    uint32_t q = slot / b.spp, si = slot - q * b.spp;
-    uint32_t px = b.x + (q % b.w), py = b.y + (q / b.w);
-    sseed += 1u;
-    // The light was chosen by k_shade_select (light-tree walk); here it is sampled.
-    LightPick pick;
-    {
-        const uint4 lp = P.light_pick[slot];
-        pick.kind = lp.x, pick.index = lp.y, pick.parent_path = lp.z, pick.selection_pdf = __uint_as_float(lp.w);
-    }
-    const float2 luv = P.light_uv[slot];
-    LightSample li;
-    sample_picked_light(S, pick, luv.x, luv.y, wl, time, is.pos, li);
-    bool found_light = false;
-    if (!(li.kind == 0 || li.pdf <= 0.0f || li.selection_pdf <= 0.0f)) {
-        V4 attenuation;
-        float closure_pdf;
-        V3 so, sd;
-        float smax;
-        V3 ng = normalized(is.nor_g);
-        V3 ldir = li.kind == 1 ? li.direction : li.pos - is.pos;
-        closure_evaluate<KIND>(is.closure, shade_ctx, ldir, attenuation, closure_pdf);
-        so = robust_ray_origin(is.pos, is.pos_err, ng, ldir);
-        if (li.kind == 1) {
-            sd = li.direction;
-            smax = CUDART_INF_F;
-        } else {
-            V3 offset_end = robust_ray_origin(li.pos, li.err, normalized(li.nor), -ldir);
-            sd = offset_end - so;
-            smax = 1.0f;
-        }
-        if (!(max_element4(attenuation) <= 0.0f)) {
-            float light_mis_pdf = power_heuristic(li.pdf, closure_pdf);
-            V4 pend = ((li.color * attenuation) * light_attenuation) / (light_mis_pdf * li.selection_pdf);
-            P.pending[slot] = to_f4(pend);
-            P.ray_o[slot] = make_float4(so.x, so.y, so.z, time);
-            P.ray_d[slot] = make_float4(sd.x, sd.y, sd.z, smax);
-            found_light = true;
-        }
-    }
-
-    // bounce (renderer.rs:598-644)
-    bool do_bounce = false;
-    uint32_t bounce_count = (flags & F_BOUNCE_MASK) >> F_BOUNCE_SHIFT;
-    V3 nb_o = mk3(0, 0, 0), nb_d = mk3(0, 0, 0);
-    V4 next_atten = from_f4(P.next_atten[slot]);
-    if (bounce_count < 2u) {
-        bounce_count += 1u;
-        sseed += 1u;
-        float b4[4];
-        get_sample_4d(si, 0, px, py, sseed, b4);
-        V3 bdir;
-        V4 filter;
-        float pdf;
-        closure_sample<KIND>(is.closure, shade_ctx, is.incoming, b4[0], b4[1], bdir, filter, pdf);
-        if ((pdf > 0.0f) && (max_element4(filter) > 0.0f)) {
-            next_atten = filter;
-            closure_sample_pdf = pdf;
-            nb_o = robust_ray_origin(is.pos, is.pos_err, normalized(is.nor_g), bdir);
-            nb_d = bdir;
-            flags |= F_HAS_NEXT;
-            do_bounce = true;
-            P.nb_o[slot] = make_float4(nb_o.x, nb_o.y, nb_o.z, 0.0f);
-            P.nb_d[slot] = make_float4(nb_d.x, nb_d.y, nb_d.z, 0.0f);
-            P.next_atten[slot] = to_f4(next_atten);
-        }
-    } else {
-        flags &= ~F_HAS_NEXT;
-    }
-    flags = (flags & ~F_BOUNCE_MASK) | (bounce_count << F_BOUNCE_SHIFT);
-    P.sseed[slot] = sseed;
-    P.closure_pdf[slot] = closure_sample_pdf;
-
-    if (found_light) {
-        flags = (flags & ~F_EVENT_MASK) | (EV_SHADOW << F_EVENT_SHIFT) | F_OCCLUSION;
-        P.flags[slot] = flags;
-        P.light_atten[slot] = to_f4(light_attenuation);
-        return true;
-    } else if (do_bounce) {
-        P.ray_o[slot] = make_float4(nb_o.x, nb_o.y, nb_o.z, time);
-        P.ray_d[slot] = make_float4(nb_d.x, nb_d.y, nb_d.z, CUDART_INF_F);
-        flags = (flags & ~(F_EVENT_MASK | F_OCCLUSION)) | (EV_BOUNCE << F_EVENT_SHIFT);
-        P.flags[slot] = flags;
-        P.light_atten[slot] = to_f4(light_attenuation * next_atten);
-        return true;
-    }
-    P.flags[slot] = flags;
-    P.light_atten[slot] = to_f4(light_attenuation);
+    static_assert(CLS == SHADE_SIMPLE || CLS == SHADE_EMIT, "surface hits are shaded by k_shade_select/_light/_bounce");
     return false;
+}
+
+#ifndef PSY_LIGHT_THREADS
+#define PSY_LIGHT_THREADS 512
+#endif
+
+// Last third of a surface hit (classes LAMBERT / GGX): the bounce sample and the path's new state
+// (renderer.rs:598-657), after k_shade_select and k_shade_light.  Survivors are appended to the next wave's
+// live list.  Like k_shade_light the block fills an SM and its warps are kept in step by barriers between the
+// big out-of-line pieces, so that the SM's warps share the instruction cache lines they run.
+template <int CLS>
+__global__ void __launch_bounds__(PSY_LIGHT_THREADS) k_shade_bounce(DScene S, PathPool P, Bucket b, ShadeQueues Q,
+                                                                    uint32_t* active_out, uint32_t* count_out) {
+    constexpr uint32_t KIND = CLS == SHADE_LAMBERT ? (uint32_t)PSY_SHADER_LAMBERT : (uint32_t)PSY_SHADER_GGX;
+    const uint32_t n = Q.count[CLS];
+    const uint32_t* __restrict__ queue = Q.q[CLS];
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const bool on = i < n;
+        const uint32_t slot = on ? queue[i] : 0u;
+        float time = 0.0f, wl = 0.0f;
+        V3 dir = mk3(0, 0, 0);
+        Isect is;
+        if (on) {
+            const HitRec h = P.hits[slot];
+            const float4 ro = P.ray_o[slot], rd = P.ray_d[slot];
+            time = ro.w;
+            wl = P.wavelength[slot];
+            dir = mk3(rd.x, rd.y, rd.z);
+            finalize_hit(S, h, mk3(ro.x, ro.y, ro.z), dir, time, is);
+        }
+        __syncthreads();
+        ShadeCtx shade_ctx;
+        if (on) shade_ctx = closure_prepare<KIND>(S, is.closure, dir, is.nor, is.nor_g, wl);
+        __syncthreads();
+        uint32_t flags = 0, sseed = 0, bounce_count = 0;
+        float b4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        bool sample_bounce = false;
+        if (on) {
+            flags = P.flags[slot];
+            sseed = P.sseed[slot] + 1u;  // the light sample's sequence (k_shade_select)
+            bounce_count = (flags & F_BOUNCE_MASK) >> F_BOUNCE_SHIFT;
+            sample_bounce = bounce_count < 2u;
+            if (sample_bounce) {
+                const uint32_t q = slot / b.spp, si = slot - q * b.spp;
+                const uint32_t px = b.x + (q % b.w), py = b.y + (q / b.w);
+                bounce_count += 1u;
+                sseed += 1u;
+                get_sample_4d(si, 0, px, py, sseed, b4);
+            }
+        }
+        __syncthreads();
+        bool alive = false;
+        if (on) {
+            float closure_sample_pdf = P.closure_pdf[slot];
+            const V4 light_attenuation = from_f4(P.light_atten[slot]) / closure_sample_pdf;
+            // the shadow ray k_shade_light prepared (the pending contribution is already in P.pending)
+            const float4 sh_o = P.sh_o[slot];
+            const bool found_light = sh_o.w != 0.0f;
+            // bounce (renderer.rs:598-644)
+            bool do_bounce = false;
+            V3 nb_o = mk3(0, 0, 0), nb_d = mk3(0, 0, 0);
+            V4 next_atten = from_f4(P.next_atten[slot]);
+            if (sample_bounce) {
+                V3 bdir;
+                V4 filter;
+                float pdf;
+                closure_sample<KIND>(is.closure, shade_ctx, is.incoming, b4[0], b4[1], bdir, filter, pdf);
+                if ((pdf > 0.0f) && (max_element4(filter) > 0.0f)) {
+                    next_atten = filter;
+                    closure_sample_pdf = pdf;
+                    nb_o = robust_ray_origin(is.pos, is.pos_err, normalized(is.nor_g), bdir);
+                    nb_d = bdir;
+                    flags |= F_HAS_NEXT;
+                    do_bounce = true;
+                    P.nb_o[slot] = make_float4(nb_o.x, nb_o.y, nb_o.z, 0.0f);
+                    P.nb_d[slot] = make_float4(nb_d.x, nb_d.y, nb_d.z, 0.0f);
+                    P.next_atten[slot] = to_f4(next_atten);
+                }
+            } else {
+                flags &= ~F_HAS_NEXT;
+            }
+            flags = (flags & ~F_BOUNCE_MASK) | (bounce_count << F_BOUNCE_SHIFT);
+            P.sseed[slot] = sseed;
+            P.closure_pdf[slot] = closure_sample_pdf;
+            if (found_light) {
+                P.ray_o[slot] = make_float4(sh_o.x, sh_o.y, sh_o.z, time);
+                P.ray_d[slot] = P.sh_d[slot];
+                flags = (flags & ~F_EVENT_MASK) | (EV_SHADOW << F_EVENT_SHIFT) | F_OCCLUSION;
+                P.light_atten[slot] = to_f4(light_attenuation);
+                alive = true;
+            } else if (do_bounce) {
+                P.ray_o[slot] = make_float4(nb_o.x, nb_o.y, nb_o.z, time);
+                P.ray_d[slot] = make_float4(nb_d.x, nb_d.y, nb_d.z, CUDART_INF_F);
+                flags = (flags & ~(F_EVENT_MASK | F_OCCLUSION)) | (EV_BOUNCE << F_EVENT_SHIFT);
+                P.light_atten[slot] = to_f4(light_attenuation * next_atten);
+                alive = true;
+            } else {
+                P.light_atten[slot] = to_f4(light_attenuation);
+            }
+            P.flags[slot] = flags;
+        }
+        // stream compaction: ballot + popc prefix + one atomic per warp (replaces the swap compaction of
+        // renderer.rs:286-295)
+        const uint32_t mask = __ballot_sync(0xffffffffu, alive);
+        uint32_t warp_base = 0;
+        if (lane == 0 && mask) warp_base = atomicAdd(count_out, __popc(mask));
+        warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+        if (alive) active_out[warp_base + __popc(mask & ((1u << lane) - 1u))] = slot;
+    }
+}
+
+// Second third of a surface hit: sample the light k_shade_select picked and evaluate the closure towards it
+// (renderer.rs:488-596).  Its own kernel for the same reason as k_shade_select: with the light sampling inline,
+// k_shade<LAMBERT> was 195 KB of straight-line code, each warp streaming through it once, and spent 11 of 17
+// cycles per issue waiting for instructions (profiles/r1n_launches.txt); the halves fit the instruction cache.
+#ifndef PSY_LIGHT_THREADS
+#define PSY_LIGHT_THREADS 512
+#endif
+// The block is as large as the registers allow (one block per SM) and its warps are kept in step by barriers
+// between the big out-of-line pieces, so that at any time all warps of an SM execute the same few KB of code.
+template <int CLS>
+__global__ void __launch_bounds__(PSY_LIGHT_THREADS) k_shade_light(DScene S, PathPool P, Bucket b, ShadeQueues Q) {
+    constexpr uint32_t KIND = CLS == SHADE_LAMBERT ? (uint32_t)PSY_SHADER_LAMBERT : (uint32_t)PSY_SHADER_GGX;
+    const uint32_t n = Q.count[CLS];
+    const uint32_t* __restrict__ queue = Q.q[CLS];
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const bool on = i < n;
+        const uint32_t slot = on ? queue[i] : 0u;
+        float time = 0.0f, wl = 0.0f;
+        V3 dir = mk3(0, 0, 0);
+        Isect is;
+        if (on) {
+            const HitRec h = P.hits[slot];
+            const float4 ro = P.ray_o[slot], rd = P.ray_d[slot];
+            time = ro.w;
+            wl = P.wavelength[slot];
+            dir = mk3(rd.x, rd.y, rd.z);
+            finalize_hit(S, h, mk3(ro.x, ro.y, ro.z), dir, time, is);
+        }
+        __syncthreads();
+        ShadeCtx shade_ctx;
+        if (on) shade_ctx = closure_prepare<KIND>(S, is.closure, dir, is.nor, is.nor_g, wl);
+        __syncthreads();
+        LightSample li;
+        li.kind = 0, li.pdf = 0.0f, li.selection_pdf = 0.0f;
+        if (on) {
+            LightPick pick;
+            const uint4 lp = P.light_pick[slot];
+            pick.kind = lp.x, pick.index = lp.y, pick.parent_path = lp.z, pick.selection_pdf = __uint_as_float(lp.w);
+            const float2 luv = P.light_uv[slot];
+            sample_picked_light(S, pick, luv.x, luv.y, wl, time, is.pos, li);
+        }
+        __syncthreads();
+        if (!on) continue;
+        const V4 light_attenuation = from_f4(P.light_atten[slot]) / P.closure_pdf[slot];
+        float4 sh_o = make_float4(0, 0, 0, 0), sh_d = make_float4(0, 0, 0, 0);
+        if (!(li.kind == 0 || li.pdf <= 0.0f || li.selection_pdf <= 0.0f)) {
+            V4 attenuation;
+            float closure_pdf;
+            V3 so, sd;
+            float smax;
+            V3 ng = normalized(is.nor_g);
+            V3 ldir = li.kind == 1 ? li.direction : li.pos - is.pos;
+            closure_evaluate<KIND>(is.closure, shade_ctx, ldir, attenuation, closure_pdf);
+            so = robust_ray_origin(is.pos, is.pos_err, ng, ldir);
+            if (li.kind == 1) {
+                sd = li.direction;
+                smax = CUDART_INF_F;
+            } else {
+                V3 offset_end = robust_ray_origin(li.pos, li.err, normalized(li.nor), -ldir);
+                sd = offset_end - so;
+                smax = 1.0f;
+            }
+            if (!(max_element4(attenuation) <= 0.0f)) {
+                float light_mis_pdf = power_heuristic(li.pdf, closure_pdf);
+                V4 pend = ((li.color * attenuation) * light_attenuation) / (light_mis_pdf * li.selection_pdf);
+                P.pending[slot] = to_f4(pend);
+                sh_o = make_float4(so.x, so.y, so.z, 1.0f);
+                sh_d = make_float4(sd.x, sd.y, sd.z, smax);
+            }
+        }
+        P.sh_o[slot] = sh_o;
+        P.sh_d[slot] = sh_d;
+    }
 }
 
 // First half of a surface hit (classes LAMBERT / GGX): the light-tree walk of Scene::sample_lights.  It is

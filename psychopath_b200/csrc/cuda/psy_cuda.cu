@@ -77,7 +77,8 @@ struct PsyScene {
     // path pool
     size_t pool_cap = 0;
     DevBuf pool_ray_o, pool_ray_d, pool_flags, pool_sseed, pool_wl, pool_cpdf, pool_nb_o, pool_nb_d, pool_next_atten,
-        pool_light_atten, pool_pending, pool_color, pool_hits, pool_light_pick, pool_light_uv, active_a, active_b;
+        pool_light_atten, pool_pending, pool_color, pool_hits, pool_light_pick, pool_light_uv, pool_sh_o, pool_sh_d,
+        active_a, active_b;
     DevBuf counts, fetch, qcounts, queues, counters, image, bucket_out, samples_out;
     DevBuf trace_scratch;  // k_trace_pool: child-reference stacks + saved parent spaces, [warp][level][ray]
     uint32_t pool_trace_blocks = 0;
@@ -210,6 +211,8 @@ PathPool make_pool(PsyScene* sc) {
     P.hits = sc->pool_hits.as<HitRec>();
     P.light_pick = sc->pool_light_pick.as<uint4>();
     P.light_uv = sc->pool_light_uv.as<float2>();
+    P.sh_o = sc->pool_sh_o.as<float4>();
+    P.sh_d = sc->pool_sh_d.as<float4>();
     return P;
 }
 
@@ -231,6 +234,8 @@ int32_t ensure_pool(PsyScene* sc, size_t n) {
     CK(sc->pool_hits.alloc(cap * sizeof(HitRec)));
     CK(sc->pool_light_pick.alloc(cap * 16));
     CK(sc->pool_light_uv.alloc(cap * 8));
+    CK(sc->pool_sh_o.alloc(cap * 16));
+    CK(sc->pool_sh_d.alloc(cap * 16));
     CK(sc->active_a.alloc(cap * 4));
     CK(sc->active_b.alloc(cap * 4));
     CK(sc->queues.alloc(cap * 4 * SHADE_CLASSES));
@@ -294,6 +299,9 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
     *launches += 1;
     uint32_t trace_blocks = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 12);
     uint32_t shade_blocks = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 16);
+    // k_shade_light: one register-limited block per SM (see kernels.cuh)
+    uint32_t light_blocks = (uint32_t)std::min<uint64_t>((n + PSY_LIGHT_THREADS - 1) / PSY_LIGHT_THREADS,
+                                                         (uint64_t)sms * std::max(1, 512 / PSY_LIGHT_THREADS));
     ShadeQueues Q;
     static const TraceTuning tune = [] {
         TraceTuning t{64, 12, 8, 8};  // measured best on the C4 scene (profiles/README.md)
@@ -330,12 +338,15 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
         uint32_t* next_count = counts + w + 1;
         k_shade<SHADE_SIMPLE><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
         k_shade<SHADE_EMIT><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
+        // surface hits: pick a light (tree walk), sample it + evaluate the closure, then bounce + path state
         k_shade_select<SHADE_LAMBERT><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q);
-        k_shade<SHADE_LAMBERT><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
+        k_shade_light<SHADE_LAMBERT><<<light_blocks, PSY_LIGHT_THREADS, 0, st>>>(sc->d, P, b, Q);
+        k_shade_bounce<SHADE_LAMBERT><<<light_blocks, PSY_LIGHT_THREADS, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
         k_shade_select<SHADE_GGX><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q);
-        k_shade<SHADE_GGX><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
+        k_shade_light<SHADE_GGX><<<light_blocks, PSY_LIGHT_THREADS, 0, st>>>(sc->d, P, b, Q);
+        k_shade_bounce<SHADE_GGX><<<light_blocks, PSY_LIGHT_THREADS, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
         stamp(ev ? &ev->shade : nullptr, false);
-        *launches += 7;
+        *launches += 9;
     }
     stamp(ev ? &ev->film : nullptr, true);
     k_film<<<(b.w * b.h + 127) / 128, 128, 0, st>>>(P, b, out, stride, ox, oy, samples_out);
