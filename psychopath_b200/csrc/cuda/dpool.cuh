@@ -58,9 +58,9 @@ enum PoolField {
     PF_MESH_PATH,
     PF_TVBASE,  // tri_verts index of triangle 0 of the current mesh, minus tri_base * 3 * keys
     PF_NK,      // vertex keys of the current mesh
-    PF_OP,      // 3 words: world origin in the ray's permuted axis order
-    PF_S = PF_OP + 3,  // 3 words: shear constants of the watertight test
-    PF_STK = PF_S + 3,  // POOL_WIN words: ring window of the stack
+    PF_WOL,     // 3+3 words: origin and 1/direction in the root assembly's space (what leaving a first-level
+                // assembly goes back to, without a trip to the scratch area)
+    PF_STK = PF_WOL + 6,  // POOL_WIN words: ring window of the stack
     PF_WORDS = PF_STK + POOL_WIN
 };
 
@@ -79,13 +79,15 @@ constexpr uint32_t RF_MSPACE_SHIFT = 20;  // space bits of the mesh-level ray (f
 constexpr uint32_t RF_MSPACE_MASK = 15u << RF_MSPACE_SHIFT;
 constexpr uint32_t RF_MCLS_SHIFT = 24;  // 2 bits: shading class of the current mesh instance
 constexpr uint32_t RF_HCLS_SHIFT = 26;  // 2 bits: shading class of the closest triangle hit so far
+constexpr uint32_t RF_WSPACE_SHIFT = 28;  // space bits of the root-level ray, 4 bits
 // path record word r0.x (dscene.cuh): kind 0-2, own 3, shading class 4-5, transform keys 8+
 constexpr uint32_t PREC_CLS_SHIFT = 4;
 
 constexpr int POOL_CTX_WORDS = 9;
 constexpr int POOL_MS_WORDS = 12;
+constexpr int POOL_RC_WORDS = 6;  // per ray: origin in permuted axis order + shear constants of the watertight test
 constexpr size_t POOL_SCRATCH_WORDS_PER_WARP =
-    (size_t)(TRACE_STACK_SIZE + POOL_CTX_WORDS * TRACE_MAX_NEST + POOL_MS_WORDS) * POOL_RAYS;
+    (size_t)(TRACE_STACK_SIZE + POOL_CTX_WORDS * TRACE_MAX_NEST + POOL_MS_WORDS + POOL_RC_WORDS) * POOL_RAYS;
 constexpr size_t POOL_SMEM_BYTES_PER_WARP = (size_t)PF_WORDS * POOL_RAYS * 4 + (size_t)Q_COUNT * POOL_RAYS;
 constexpr size_t POOL_SMEM_BYTES = POOL_SMEM_BYTES_PER_WARP * POOL_WARPS;
 
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
     uint32_t* const stk = scratch + (size_t)(blockIdx.x * POOL_WARPS + warp) * POOL_SCRATCH_WORDS_PER_WARP;
     uint32_t* const ctxb = stk + TRACE_STACK_SIZE * R;            // saved parent spaces of nested assemblies
     uint32_t* const msb = ctxb + POOL_CTX_WORDS * TRACE_MAX_NEST * R;  // local->world of the current mesh
+    uint32_t* const rcb = msb + POOL_MS_WORDS * R;                     // per-ray constants of the triangle test
     const uint32_t n_rays = *count;
 
     struct {
@@ -145,11 +148,21 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
         ++sp;                                      \
         lo = sp > lo + POOL_WIN ? sp - POOL_WIN : lo; \
     }
-// (popping an entry from below the mesh entry's stack height leaves the mesh instance: no marker needed)
+// Leaving the first-level assembly (tracer.rs:131-148): back to the root assembly's ray, which never left
+// shared memory.
+#define PSY_LEAVE_LEVEL1()                                                                          \
+    {                                                                                               \
+        flags = (flags & ~(RF_CTXN_MASK | RF_SPACE_MASK)) | (((flags >> RF_WSPACE_SHIFT) & 15u) << 1); \
+        ST(PF_PATH_BASE, r) = 0u;                                                                   \
+        ST(PF_INST_BASE, r) = S.root_instance_base;                                                 \
+        _Pragma("unroll") for (int w_ = 0; w_ < 6; ++w_) ST(PF_OL + w_, r) = ST(PF_WOL + w_, r);    \
+    }
+// (popping an entry from below the mesh entry's / first-level assembly's stack height leaves it: no marker needed)
 #define PSY_POP(out)                                \
     {                                               \
         --sp;                                       \
         if (sp < msp) flags &= ~RF_IN_MESH;         \
+        if ((flags & (RF_CTXN_MASK | RF_IN_MESH)) == (1u << RF_CTXN_SHIFT) && sp < asp) PSY_LEAVE_LEVEL1() \
         if (sp < lo) {                              \
             lo = sp;                                \
             out = stk[sp * R + r];                  \
@@ -160,7 +173,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
 #define PSY_LOAD_SP()                                          \
     {                                                          \
         const uint32_t spw = ST(PF_SP, r);                     \
-        sp = spw & 255u, lo = (spw >> 8) & 255u, msp = spw >> 16; \
+        sp = spw & 255u, lo = (spw >> 8) & 255u, msp = (spw >> 16) & 255u, asp = spw >> 24; \
     }
 
     for (;;) {
@@ -231,7 +244,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
         }
 
         // state every remaining step kind works on
-        uint32_t flags = 0, top = PSY_NONE, sp = 0, lo = 0, msp = 0;
+        uint32_t flags = 0, top = PSY_NONE, sp = 0, lo = 0, msp = 0, asp = 0;
         bool to_light = false;  // an instance entry that turned out to be a light: handled by the light step
 
         if (k == Q_FREE) {
@@ -252,8 +265,8 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 const RayTriPre pre = tri_precompute(dir);
                 const V3 op = permute3(orig, pre);
                 const LocalRay lr = make_local_ray(xf_identity(), orig, dir);  // evaluated literally, like the reference
-                flags = ((P.flags[slot] & F_OCCLUSION) ? RF_OCCL : 0u) | (lr.bits << 1) | RF_SPACE_EMPTY |
-                        ((uint32_t)PSY_HIT_MISS << RF_HIT_SHIFT) |
+                flags = ((P.flags[slot] & F_OCCLUSION) ? RF_OCCL : 0u) | (lr.bits << 1) | (lr.bits << RF_WSPACE_SHIFT) |
+                        RF_SPACE_EMPTY | ((uint32_t)PSY_HIT_MISS << RF_HIT_SHIFT) |
                         (((uint32_t)pre.xi | ((uint32_t)pre.yi << 2) | ((uint32_t)pre.zi << 4)) << RF_PERM_SHIFT);
                 ST(PF_SLOT, r) = slot;
                 ST(PF_MAXT, r) = __float_as_uint(rd.w);
@@ -264,10 +277,12 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 ST(PF_DI + 2, r) = __float_as_uint(lr.di.z);
                 ST(PF_PATH_BASE, r) = 0u;
                 ST(PF_INST_BASE, r) = S.root_instance_base;
-                ST(PF_OP + 0, r) = __float_as_uint(op.x), ST(PF_OP + 1, r) = __float_as_uint(op.y);
-                ST(PF_OP + 2, r) = __float_as_uint(op.z);
-                ST(PF_S + 0, r) = __float_as_uint(pre.sx), ST(PF_S + 1, r) = __float_as_uint(pre.sy);
-                ST(PF_S + 2, r) = __float_as_uint(pre.sz);
+#pragma unroll
+                for (int w = 0; w < 6; ++w) ST(PF_WOL + w, r) = ST(PF_OL + w, r);
+                rcb[0 * R + r] = __float_as_uint(op.x), rcb[1 * R + r] = __float_as_uint(op.y);
+                rcb[2 * R + r] = __float_as_uint(op.z);
+                rcb[3 * R + r] = __float_as_uint(pre.sx), rcb[4 * R + r] = __float_as_uint(pre.sy);
+                rcb[5 * R + r] = __float_as_uint(pre.sz);
                 top = S.root_bvh;
             }
         } else if (k == Q_NODE) {
@@ -276,11 +291,27 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 const uint32_t ref = ST(PF_TOP, r);
                 const uint4* np = S.nodes + (size_t)ref * 8u;
                 // the whole 128-byte node at once (the static bounds are unused, but valid memory, for motion nodes)
+#if PSY_POOL_NODE_TEX
+                // experiment: node fetches through the texture pipe, next to the LSU pipe that carries everything else
+                const int tn = (int)(ref * 8u);
+                const uint4 child = tex1Dfetch<uint4>(S.nodes_tex, tn);
+                const uint4 meta = tex1Dfetch<uint4>(S.nodes_tex, tn + 1);
+#define PSY_TEXF4(i)                                                                                          \
+    ([&] {                                                                                                    \
+        const uint4 t = tex1Dfetch<uint4>(S.nodes_tex, tn + (i));                                             \
+        return make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w)); \
+    }())
+                float4 bx0 = PSY_TEXF4(2), bx1 = PSY_TEXF4(3), by0 = PSY_TEXF4(4), by1 = PSY_TEXF4(5), bz0 = PSY_TEXF4(6),
+                       bz1 = PSY_TEXF4(7);
+#undef PSY_TEXF4
+                (void)np;
+#else
                 const uint4 child = __ldg(np);
                 const uint4 meta = __ldg(np + 1);  // traversal_code, n_keys, key_base, n_children
                 const float4* bp = reinterpret_cast<const float4*>(np + 2);
                 float4 bx0 = __ldg(bp), bx1 = __ldg(bp + 1), by0 = __ldg(bp + 2), by1 = __ldg(bp + 3), bz0 = __ldg(bp + 4),
                        bz1 = __ldg(bp + 5);
+#endif
                 flags = ST(PF_FLAGS, r);
                 PSY_LOAD_SP()
                 const bool in_mesh = (flags & RF_IN_MESH) != 0u;
@@ -405,7 +436,10 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                     pre.xi = (int)((flags >> RF_PERM_SHIFT) & 3u);
                     pre.yi = (int)((flags >> (RF_PERM_SHIFT + 2)) & 3u);
                     pre.zi = (int)((flags >> (RF_PERM_SHIFT + 4)) & 3u);
-                    pre.sx = STF(PF_S + 0, r), pre.sy = STF(PF_S + 1, r), pre.sz = STF(PF_S + 2, r);
+                    const V3 op = mk3(__uint_as_float(rcb[0 * R + r]), __uint_as_float(rcb[1 * R + r]),
+                                      __uint_as_float(rcb[2 * R + r]));
+                    pre.sx = __uint_as_float(rcb[3 * R + r]), pre.sy = __uint_as_float(rcb[4 * R + r]);
+                    pre.sz = __uint_as_float(rcb[5 * R + r]);
                     if (!(flags & RF_SPACE_EMPTY)) {
                         const uint32_t* m = msb + r;
                         Xf ms;
@@ -418,7 +452,6 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                         p0 = permute3(p0, pre), p1 = permute3(p1, pre), p2 = permute3(p2, pre);
                     }
                     if (COUNT) cnt.tri_tests += 1;
-                    const V3 op = mk3(STF(PF_OP + 0, r), STF(PF_OP + 1, r), STF(PF_OP + 2, r));
                     float t, b0, b1, b2;
                     if (tri_intersect_perm(op, pre, STF(PF_MAXT, r), p0, p1, p2, t, b0, b1, b2)) {
                         if (flags & RF_OCCL) {
@@ -473,9 +506,10 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 } else if (mesh || (kind == PATH_ASSEMBLY && ctx_n < (uint32_t)TRACE_MAX_NEST)) {
                     // Mesh and assembly entries share everything expensive (the ray in the instance's space),
                     // so the lanes of both kinds run it together.
-                    if (!mesh) {
-                        // save the parent space (leaving the assembly is a reload: same inputs, same bits as the
-                        // reference's second update_local, tracer.rs:131-148)
+                    if (!mesh && ctx_n != 0u) {
+                        // nested deeper than one level: save the parent space (leaving the assembly is a reload: same
+                        // inputs, same bits as the reference's second update_local, tracer.rs:131-148).  The root
+                        // level needs no saving: its ray stays in PF_WOL.
                         uint32_t* c = ctxb + (size_t)(ctx_n * POOL_CTX_WORDS) * R + r;
                         c[0 * R] = ST(PF_PATH_BASE, r);
                         c[1 * R] = ST(PF_INST_BASE, r);
@@ -530,6 +564,8 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                     }
                     if (mesh) {
                         msp = sp;  // whatever is popped from below this height is outside the mesh
+                    } else if (ctx_n == 0u) {
+                        asp = sp;  // ... and outside the first-level assembly
                     } else {
                         PSY_PUSH(MARK_POP_ASM)
                     }
@@ -541,7 +577,8 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                     pre.xi = (int)((flags >> RF_PERM_SHIFT) & 3u);
                     pre.yi = (int)((flags >> (RF_PERM_SHIFT + 2)) & 3u);
                     pre.zi = (int)((flags >> (RF_PERM_SHIFT + 4)) & 3u);
-                    pre.sx = STF(PF_S + 0, r), pre.sy = STF(PF_S + 1, r), pre.sz = STF(PF_S + 2, r);
+                    pre.sx = __uint_as_float(rcb[3 * R + r]), pre.sy = __uint_as_float(rcb[4 * R + r]);
+                    pre.sz = __uint_as_float(rcb[5 * R + r]);
                     const LightHit lh =
                         light_instance_hit_inline(S.lights, S.light_shape, r1.x, kind, xform, orig, dir, ol, time, max_t, pre);
                     if (COUNT) cnt.tri_tests += lh.tri_tests;
@@ -584,7 +621,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 if (sp > 0u) PSY_POP(top)
             }
             ST(PF_TOP, r) = top;
-            ST(PF_SP, r) = sp | (lo << 8) | (msp << 16);
+            ST(PF_SP, r) = sp | (lo << 8) | (msp << 16) | (asp << 24);
             ST(PF_FLAGS, r) = flags;
             dest = top == PSY_NONE ? Q_DONE : (!(top & PSY_CHILD_LEAF_BIT) ? Q_NODE : ((flags & RF_IN_MESH) ? Q_TRI : Q_INST));
         }
@@ -605,6 +642,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
 #undef STF
 #undef PSY_PUSH
 #undef PSY_POP
+#undef PSY_LEAVE_LEVEL1
 #undef PSY_LOAD_SP
     if (COUNT) {
         atomicAdd(&counters->node_visits, (unsigned long long)cnt.node_visits);

@@ -30,9 +30,16 @@ struct DMesh {
     uint32_t has_normals, pad;
 };
 
+// k_trace_pool fetches BVH4 nodes through the texture pipe (tex1Dfetch on a linear uint4 texture over `nodes`):
+// its LSU pipe is ~70 % busy with the scattered state / stack traffic, the TEX pipe is otherwise idle (+4 % on C5).
+#ifndef PSY_POOL_NODE_TEX
+#define PSY_POOL_NODE_TEX 1
+#endif
+
 struct DScene {
     // acceleration structures
     const uint4* nodes;          // PsyBvh4Node as 8 x 16 B
+    unsigned long long nodes_tex; // the same buffer as a linear uint4 texture object (PSY_POOL_NODE_TEX)
     const float4* motion_bounds; // PsyBBox4 as 6 x float4 per key
     // geometry: per triangle (leaf order) 3*k float4: [v0 keys][v1 keys][v2 keys]; v0-key0 .w = original index
     const float4* tri_verts;

@@ -89,6 +89,7 @@ struct PsyScene {
     uint64_t last_trace_launches = 0;
     std::mutex mu;
     ~PsyScene() {
+        if (d.nodes_tex) cudaDestroyTextureObject((cudaTextureObject_t)d.nodes_tex);
         for (auto e : events) cudaEventDestroy(e);
     }
 };
@@ -765,6 +766,21 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
 
     DScene& d = sc->d;
     d.nodes = sc->nodes.as<uint4>();
+    d.nodes_tex = 0;
+#if PSY_POOL_NODE_TEX
+    {
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = sc->nodes.p;
+        rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+        rd.res.linear.sizeInBytes = (size_t)s->n_nodes * sizeof(PsyBvh4Node);
+        cudaTextureDesc td{};
+        td.readMode = cudaReadModeElementType;
+        cudaTextureObject_t tex = 0;
+        if (s->n_nodes) CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+        d.nodes_tex = tex;
+    }
+#endif
     d.motion_bounds = sc->motion.as<float4>();
     d.tri_verts = sc->tri_verts.as<float4>();
     d.tris = sc->tris.as<uint4>();
