@@ -107,3 +107,72 @@ Scene $fixture {
     }
 }
 """
+
+
+def nested_assemblies_text():
+    """Assemblies nested three deep (root -> $town -> $block -> $house -> meshes / lights), with and without
+    transforms of their own and with transform motion at two levels: exercises every way of entering and leaving
+    an instance (first level: kept in shared memory by k_trace_pool; deeper: saved to the scratch area)."""
+    return """
+Scene $nested {
+    Output { Path ["nested.png"] }
+    RenderSettings { Resolution [96 64] SamplesPerPixel [8] Seed [11] }
+    Camera {
+        Fov [55.0]
+        FocalDistance [12.0]
+        ApertureRadius [0.02]
+        Transform [1 0 0 0  0 0 1 0  0 1 0 0  0 -12 3 1]
+    }
+    World {
+        BackgroundShader { Type [Color] Color [rec709, 0.08 0.09 0.12] }
+        DistantDiskLight $sun { Direction [-0.2 0.5 -0.8] Color [rec709, 1.2 1.1 1.0] Radius [0.04] }
+    }
+    Assembly {
+        SurfaceShader $grey { Type [Lambert] Color [rec709, 0.6 0.6 0.6] }
+        MeshSurface $ground {
+            Vertices [-12 -12 0  12 -12 0  12 12 0  -12 12 0]
+            FaceVertCounts [4]
+            FaceVertIndices [0 1 2 3]
+        }
+        Assembly $town {
+            SurfaceShader $brick { Type [Lambert] Color [rec709, 0.7 0.3 0.2] }
+            Assembly $block {
+                SurfaceShader $steel { Type [GGX] Color [rec709, 0.8 0.8 0.9] Roughness [0.3] Fresnel [0.5] }
+                Assembly $house {
+                    SurfaceShader $brick { Type [Lambert] Color [rec709, 0.7 0.3 0.2] }
+                    SurfaceShader $steel { Type [GGX] Color [rec709, 0.8 0.8 0.9] Roughness [0.3] Fresnel [0.5] }
+                    MeshSurface $walls {
+                        Vertices [-0.5 -0.5 0  0.5 -0.5 0  0.5 0.5 0  -0.5 0.5 0  -0.5 -0.5 1  0.5 -0.5 1  0.5 0.5 1  -0.5 0.5 1]
+                        FaceVertCounts [4 4 4 4 4 4]
+                        FaceVertIndices [0 3 2 1  4 5 6 7  0 1 5 4  1 2 6 5  2 3 7 6  3 0 4 7]
+                    }
+                    MeshSurface $roof {
+                        Vertices [-0.6 -0.6 1  0.6 -0.6 1  0.6 0.6 1  -0.6 0.6 1  0 0 1.7]
+                        Vertices [-0.6 -0.6 1  0.6 -0.6 1  0.6 0.6 1  -0.6 0.6 1  0.1 0 1.8]
+                        FaceVertCounts [3 3 3 3]
+                        FaceVertIndices [0 1 4  1 2 4  2 3 4  3 0 4]
+                    }
+                    SphereLight $porch { Color [rec709, 6 5 4] Radius [0.1] }
+                    Instance { Data [$walls] SurfaceShaderBind [$brick] }
+                    Instance { Data [$roof] SurfaceShaderBind [$steel] Transform [1 0 0 0  0 1 0 0  0 0 1 0  0 0 -0.02 1] }
+                    Instance { Data [$porch] Transform [1 0 0 0  0 1 0 0  0 0 1 0  0 0.8 -0.6 1] }
+                }
+                RectangleLight $lamp { Color [rec709, 9 9 10] Dimensions [0.6 0.4] }
+                Instance { Data [$house] }
+                Instance { Data [$house] Transform [0.8 0.6 0 0  -0.6 0.8 0 0  0 0 1 0  -1.6 0.2 0 1] }
+                Instance { Data [$house]
+                    Transform [0.7 0 0 0  0 0.7 0 0  0 0 0.7 0  1.2 0.4 0 1]
+                    Transform [0.7 0 0 0  0 0.7 0 0  0 0 0.7 0  1.3 0.4 -0.1 1] }
+                Instance { Data [$lamp] Transform [1 0 0 0  0 -1 0 0  0 0 -1 0  0 0 2.5 1] }
+            }
+            Instance { Data [$block] Transform [1 0 0 0  0 1 0 0  0 0 1 0  -2.5 0 0 1] }
+            Instance { Data [$block] Transform [0 1 0 0  -1 0 0 0  0 0 1 0  2.5 1 0 1] Transform [0 1 0 0  -1 0 0 0  0 0 1 0  2.7 1 0 1] }
+            Instance { Data [$block] }
+        }
+        Instance { Data [$ground] SurfaceShaderBind [$grey] }
+        Instance { Data [$town] Transform [1 0 0 0  0 1 0 0  0 0 1 0  0 2 0 1] }
+        Instance { Data [$town] Transform [0.9 0 0 0  0 0.9 0 0  0 0 0.9 0  6 -3 0 1] Transform [0.9 0 0 0  0 0.9 0 0  0 0 0.9 0  6 -3.3 0 1] }
+        Instance { Data [$town] }
+    }
+}
+"""

@@ -9,7 +9,7 @@ import pytest
 
 import oracle_lib as O
 from psychopath_b200 import abi, api
-from scenes import cornell_text, cube_text, motion_instances_text
+from scenes import cornell_text, cube_text, motion_instances_text, nested_assemblies_text
 
 pytestmark = pytest.mark.gpu
 
@@ -22,6 +22,8 @@ def make_scene(name):
         s = api.Scene.from_psy_string(cube_text(res=(160, 90), spp=4, camera_motion=True))
     elif name == "fixture":
         s = api.Scene.from_psy_string(motion_instances_text())
+    elif name == "nested":
+        s = api.Scene.from_psy_string(nested_assemblies_text())
     elif name == "instanced":
         s = api.Scene.synth_instanced(asset_quads=24, n_assets=3, n_clusters=9, inst_per_cluster=5,
                                       lights_per_cluster=4, cluster_xform_keys=2, res=(96, 54), spp=4, seed=4)
@@ -36,7 +38,7 @@ def make_scene(name):
     return s
 
 
-SCENES = ["cornell", "cube_dof_motion", "fixture", "instanced", "grid_motion", "deep_instanced"]
+SCENES = ["cornell", "cube_dof_motion", "fixture", "nested", "instanced", "grid_motion", "deep_instanced"]
 
 
 def probe_rays(scene, n_random=20000, seed=123):
