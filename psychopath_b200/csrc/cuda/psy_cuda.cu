@@ -350,7 +350,8 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
         *launches += 9;
     }
     stamp(ev ? &ev->film : nullptr, true);
-    k_film<<<(b.w * b.h + 127) / 128, 128, 0, st>>>(P, b, out, stride, ox, oy, samples_out);
+    k_film<<<(b.w * b.h + 32 * FILM_WARPS - 1) / (32 * FILM_WARPS), 32 * FILM_WARPS, 0, st>>>(P, b, out, stride, ox, oy,
+                                                                                              samples_out);
     stamp(ev ? &ev->film : nullptr, false);
     *launches += 1;
     CK(cudaGetLastError());

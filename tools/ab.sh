@@ -6,6 +6,6 @@ for v in "$@"; do
   echo "$out" | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); s=d['stage_ms_per_step_rank0']
-print('$label', 'Mrays/s=%.1f'%d['value'], 'trace=%.1f'%s['trace_ms'], 'shade=%.1f'%s['shade_ms'], 'ms/step=%.1f'%d['ms_per_step'])
+print('$label', 'Mrays/s=%.1f'%d['value'], 'trace=%.1f'%s['trace_ms'], 'shade=%.1f'%s['shade_ms'], 'film=%.1f'%s['film_ms'], 'gen=%.1f'%s['generate_ms'], 'ms/step=%.1f'%d['ms_per_step'])
 "
 done
