@@ -336,11 +336,22 @@ def main():
         pk, pk_kind = peaks()
         _, cst = r.render(max_samples_per_bucket=args.pool, spp=min(args.counter_spp, spp), counters=True,
                           device_resident_only=True)
-        b_ray, per_ray = algorithmic_bytes_per_ray(cst, keys_xform=1)
+        # every instance path of these scenes carries the cluster's transform keys (32 + 48*k_x per entry)
+        b_ray, per_ray = algorithmic_bytes_per_ray(cst, keys_xform=int(kw.get("cluster_xform_keys", 1)))
         my_rays = int(t[1])
         achieved = (my_rays * b_ray) / max(float(t[3]) * 1e-3, 1e-12) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+        # DRAM bytes of the trace kernel per launch: bytes per ray from the committed ncu capture of the same
+        # scene (profiles/r1_trace_dram.json) x the rays one launch of this run traces on average
+        traffic, traffic_note = None, None
+        tp = os.path.join(REPO, "profiles", "r1_trace_dram.json")
+        if os.path.exists(tp) and name == "C5":
+            td = json.load(open(tp))
+            traffic = td["dram_bytes_per_ray"] * my_rays / max(float(t[4]), 1.0)
+            traffic_note = "ncu dram__bytes_read+write per ray (%.0f B, profiles/r1_trace_dram.json) x rays per launch; " \
+                           "algorithmic bytes per launch: %.3g" % (td["dram_bytes_per_ray"], b_ray * my_rays / max(float(t[4]), 1.0))
+        roofline = {"bound": "hbm", "kernel": "k_trace_pool", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "traffic_note": traffic_note,
+                    "peak_kind": pk_kind,
                     "bytes_per_ray": b_ray, "per_ray": per_ray,
                     "trace_ms_per_step": float(t[3]) / args.steps, "trace_launches_per_step": float(t[4]) / args.steps,
                     "trace_share_of_step": float(t[3]) * 1e-3 / dev_s,
