@@ -41,6 +41,10 @@ struct PathPool {
     float2* light_uv;   // the two light-sampling random numbers of the same Sobol vector
     float4* sh_o;       // k_shade_light -> k_shade: shadow ray origin, w = 1 when a light sample was found
     float4* sh_d;       // shadow ray direction, w = max_t
+    // k_shade_light -> k_shade_bounce: what the bounce needs of the finalised hit and the prepared closure, so that
+    // neither is computed twice: (pos, pos_err) (nor_g, roughness) (incoming, fresnel) (spectral colour)
+    // (flipped shading normal) (flipped geometric normal)
+    float4* ic[6];
 };
 
 struct Bucket {
@@ -376,21 +380,23 @@ __global__ void __launch_bounds__(PSY_LIGHT_THREADS) k_shade_bounce(DScene S, Pa
         const uint32_t i = base + threadIdx.x;
         const bool on = i < n;
         const uint32_t slot = on ? queue[i] : 0u;
-        float time = 0.0f, wl = 0.0f;
-        V3 dir = mk3(0, 0, 0);
+        float time = 0.0f;
         Isect is;
-        if (on) {
-            const HitRec h = P.hits[slot];
-            const float4 ro = P.ray_o[slot], rd = P.ray_d[slot];
-            time = ro.w;
-            wl = P.wavelength[slot];
-            dir = mk3(rd.x, rd.y, rd.z);
-            finalize_hit(S, h, mk3(ro.x, ro.y, ro.z), dir, time, is);
-        }
-        __syncthreads();
         ShadeCtx shade_ctx;
-        if (on) shade_ctx = closure_prepare<KIND>(S, is.closure, dir, is.nor, is.nor_g, wl);
-        __syncthreads();
+        if (on) {
+            // the finalised hit and the prepared closure, as k_shade_light left them
+            const float4 c0 = P.ic[0][slot], c1 = P.ic[1][slot], c2 = P.ic[2][slot], c3 = P.ic[3][slot],
+                         c4 = P.ic[4][slot], c5 = P.ic[5][slot];
+            time = P.ray_o[slot].w;
+            is.pos = mk3(c0.x, c0.y, c0.z), is.pos_err = c0.w;
+            is.nor_g = mk3(c1.x, c1.y, c1.z), is.closure.roughness = c1.w;
+            is.incoming = mk3(c2.x, c2.y, c2.z), is.closure.fresnel = c2.w;
+            shade_ctx.spec = from_f4(c3);
+            shade_ctx.nn = mk3(c4.x, c4.y, c4.z);
+            shade_ctx.fng = mk3(c5.x, c5.y, c5.z);
+            shade_ctx.aa = mk3(0, 0, 0);
+            if (KIND == (uint32_t)PSY_SHADER_GGX) shade_ctx.aa = -normalized(is.incoming);
+        }
         uint32_t flags = 0, sseed = 0, bounce_count = 0;
         float b4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         bool sample_bounce = false;
@@ -499,7 +505,15 @@ __global__ void __launch_bounds__(PSY_LIGHT_THREADS) k_shade_light(DScene S, Pat
         }
         __syncthreads();
         ShadeCtx shade_ctx;
-        if (on) shade_ctx = closure_prepare<KIND>(S, is.closure, dir, is.nor, is.nor_g, wl);
+        if (on) {
+            shade_ctx = closure_prepare<KIND>(S, is.closure, dir, is.nor, is.nor_g, wl);
+            P.ic[0][slot] = make_float4(is.pos.x, is.pos.y, is.pos.z, is.pos_err);
+            P.ic[1][slot] = make_float4(is.nor_g.x, is.nor_g.y, is.nor_g.z, is.closure.roughness);
+            P.ic[2][slot] = make_float4(is.incoming.x, is.incoming.y, is.incoming.z, is.closure.fresnel);
+            P.ic[3][slot] = to_f4(shade_ctx.spec);
+            P.ic[4][slot] = make_float4(shade_ctx.nn.x, shade_ctx.nn.y, shade_ctx.nn.z, 0.0f);
+            P.ic[5][slot] = make_float4(shade_ctx.fng.x, shade_ctx.fng.y, shade_ctx.fng.z, 0.0f);
+        }
         __syncthreads();
         LightSample li;
         li.kind = 0, li.pdf = 0.0f, li.selection_pdf = 0.0f;

@@ -77,7 +77,7 @@ struct PsyScene {
     // path pool
     size_t pool_cap = 0;
     DevBuf pool_ray_o, pool_ray_d, pool_flags, pool_sseed, pool_wl, pool_cpdf, pool_nb_o, pool_nb_d, pool_next_atten,
-        pool_light_atten, pool_pending, pool_color, pool_hits, pool_light_pick, pool_light_uv, pool_sh_o, pool_sh_d,
+        pool_light_atten, pool_pending, pool_color, pool_hits, pool_light_pick, pool_light_uv, pool_sh_o, pool_sh_d, pool_ic,
         active_a, active_b;
     DevBuf counts, fetch, qcounts, queues, counters, image, bucket_out, samples_out;
     DevBuf trace_scratch;  // k_trace_pool: child-reference stacks + saved parent spaces, [warp][level][ray]
@@ -214,6 +214,7 @@ PathPool make_pool(PsyScene* sc) {
     P.light_uv = sc->pool_light_uv.as<float2>();
     P.sh_o = sc->pool_sh_o.as<float4>();
     P.sh_d = sc->pool_sh_d.as<float4>();
+    for (int k = 0; k < 6; ++k) P.ic[k] = sc->pool_ic.as<float4>() + (size_t)k * sc->pool_cap;
     return P;
 }
 
@@ -237,6 +238,7 @@ int32_t ensure_pool(PsyScene* sc, size_t n) {
     CK(sc->pool_light_uv.alloc(cap * 8));
     CK(sc->pool_sh_o.alloc(cap * 16));
     CK(sc->pool_sh_d.alloc(cap * 16));
+    CK(sc->pool_ic.alloc(cap * 16 * 6));
     CK(sc->active_a.alloc(cap * 4));
     CK(sc->active_b.alloc(cap * 4));
     CK(sc->queues.alloc(cap * 4 * SHADE_CLASSES));
@@ -300,6 +302,8 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
     *launches += 1;
     uint32_t trace_blocks = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 12);
     uint32_t shade_blocks = (uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 16);
+    // k_shade_bounce is small since it reads the hit / closure k_shade_light prepared: 3 x 256 threads per SM
+    uint32_t bounce_blocks = (uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 3);
     // k_shade_light: one register-limited block per SM (see kernels.cuh)
     uint32_t light_blocks = (uint32_t)std::min<uint64_t>((n + PSY_LIGHT_THREADS - 1) / PSY_LIGHT_THREADS,
                                                          (uint64_t)sms * std::max(1, 512 / PSY_LIGHT_THREADS));
@@ -342,10 +346,10 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
         // surface hits: pick a light (tree walk), sample it + evaluate the closure, then bounce + path state
         k_shade_select<SHADE_LAMBERT><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q);
         k_shade_light<SHADE_LAMBERT><<<light_blocks, PSY_LIGHT_THREADS, 0, st>>>(sc->d, P, b, Q);
-        k_shade_bounce<SHADE_LAMBERT><<<light_blocks, PSY_LIGHT_THREADS, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
+        k_shade_bounce<SHADE_LAMBERT><<<bounce_blocks, 256, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
         k_shade_select<SHADE_GGX><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q);
         k_shade_light<SHADE_GGX><<<light_blocks, PSY_LIGHT_THREADS, 0, st>>>(sc->d, P, b, Q);
-        k_shade_bounce<SHADE_GGX><<<light_blocks, PSY_LIGHT_THREADS, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
+        k_shade_bounce<SHADE_GGX><<<bounce_blocks, 256, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
         stamp(ev ? &ev->shade : nullptr, false);
         *launches += 9;
     }
