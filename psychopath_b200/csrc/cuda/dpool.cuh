@@ -229,16 +229,8 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 qs[Q_FREE * R + QLEN(Q_FREE) + lane] = (uint8_t)r;
             }
             qn += (uint64_t)n << (8 * Q_FREE);
-#pragma unroll
-            for (int c = 0; c < SHADE_CLASSES; ++c) {
-                const uint32_t mask = __ballot_sync(FULL, cls == c);
-                if (mask) {
-                    uint32_t qb = 0;
-                    if (lane == 0) qb = atomicAdd(Q.count + c, __popc(mask));
-                    qb = __shfl_sync(FULL, qb, 0);
-                    if (cls == c) Q.q[c][qb + __popc(mask & lt)] = slot;
-                }
-            }
+            // the path's shading class; the class queues are built from these bytes in slot order (dpartition.cuh)
+            if (cls >= 0) P.cls[slot] = (uint8_t)cls;
             __syncwarp();
             continue;
         }

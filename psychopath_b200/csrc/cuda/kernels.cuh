@@ -45,6 +45,10 @@ struct PathPool {
     // neither is computed twice: (pos, pos_err) (nor_g, roughness) (incoming, fresnel) (spectral colour)
     // (flipped shading normal) (flipped geometric normal)
     float4* ic[6];
+    // one byte per slot, 0xFF when idle: the shading class of the ray traced in this wave (k_trace* -> class queues),
+    // and 0 for a path that continues (shade kernels -> next wave's live list); see dpartition.cuh
+    uint8_t* cls;
+    uint8_t* alive;
 };
 
 struct Bucket {
@@ -186,17 +190,8 @@ __global__ void __launch_bounds__(128, PSY_TRACE_MIN_BLOCKS) k_trace(DScene S, P
                 cls = kind == PSY_SHADER_LAMBERT ? SHADE_LAMBERT : (kind == PSY_SHADER_GGX ? SHADE_GGX : SHADE_EMIT);
             }
         }
-        // one queue per shading class: warp ballot + popc prefix + one atomic per warp and class
-#pragma unroll
-        for (int c = 0; c < SHADE_CLASSES; ++c) {
-            uint32_t mask = __ballot_sync(0xffffffffu, cls == c);
-            if (mask) {
-                uint32_t qb = 0;
-                if (lane == 0) qb = atomicAdd(Q.count + c, __popc(mask));
-                qb = __shfl_sync(0xffffffffu, qb, 0);
-                if (cls == c) Q.q[c][qb + __popc(mask & ((1u << lane) - 1u))] = slot;
-            }
-        }
+        // the path's shading class; the class queues are built from these bytes in slot order (dpartition.cuh)
+        if (cls >= 0) P.cls[slot] = (uint8_t)cls;
     }
     if (COUNT) {
         atomicAdd(&counters->node_visits, cnt.node_visits);
@@ -464,13 +459,9 @@ __global__ void __launch_bounds__(PSY_LIGHT_THREADS) k_shade_bounce(DScene S, Pa
             }
             P.flags[slot] = flags;
         }
-        // stream compaction: ballot + popc prefix + one atomic per warp (replaces the swap compaction of
-        // renderer.rs:286-295)
-        const uint32_t mask = __ballot_sync(0xffffffffu, alive);
-        uint32_t warp_base = 0;
-        if (lane == 0 && mask) warp_base = atomicAdd(count_out, __popc(mask));
-        warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
-        if (alive) active_out[warp_base + __popc(mask & ((1u << lane) - 1u))] = slot;
+        // survivors: one byte per slot; the next wave's live list is built from them in slot order
+        // (dpartition.cuh; replaces the swap compaction of renderer.rs:286-295)
+        if (alive) P.alive[slot] = 0;
     }
 }
 
@@ -599,13 +590,7 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, PathPool P, Bucket b, S
             slot = queue[i];
             alive = path_next<CLS>(S, P, slot, b);
         }
-        // stream compaction: ballot + popc prefix + one atomic per warp (replaces the swap
-        // compaction of renderer.rs:286-295)
-        uint32_t mask = __ballot_sync(0xffffffffu, alive);
-        uint32_t warp_base = 0;
-        if (lane == 0 && mask) warp_base = atomicAdd(count_out, __popc(mask));
-        warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
-        if (alive) active_out[warp_base + __popc(mask & ((1u << lane) - 1u))] = slot;
+        if (alive) P.alive[slot] = 0;  // see k_shade_bounce
     }
 }
 
@@ -657,4 +642,5 @@ __global__ void __launch_bounds__(32 * FILM_WARPS) k_film(PathPool P, Bucket b, 
 
 }  // namespace psyd
 
+#include "dpartition.cuh"
 #include "dpool.cuh"

@@ -80,6 +80,7 @@ struct PsyScene {
         pool_light_atten, pool_pending, pool_color, pool_hits, pool_light_pick, pool_light_uv, pool_sh_o, pool_sh_d, pool_ic,
         active_a, active_b;
     DevBuf counts, fetch, qcounts, queues, counters, image, bucket_out, samples_out;
+    DevBuf pool_cls, pool_alive, part_tmp;  // per-slot byte columns and the block counts of the ordered partition
     DevBuf trace_scratch;  // k_trace_pool: child-reference stacks + saved parent spaces, [warp][level][ray]
     uint32_t pool_trace_blocks = 0;
     size_t counts_cap = 0;
@@ -215,6 +216,8 @@ PathPool make_pool(PsyScene* sc) {
     P.sh_o = sc->pool_sh_o.as<float4>();
     P.sh_d = sc->pool_sh_d.as<float4>();
     for (int k = 0; k < 6; ++k) P.ic[k] = sc->pool_ic.as<float4>() + (size_t)k * sc->pool_cap;
+    P.cls = sc->pool_cls.as<uint8_t>();
+    P.alive = sc->pool_alive.as<uint8_t>();
     return P;
 }
 
@@ -239,6 +242,11 @@ int32_t ensure_pool(PsyScene* sc, size_t n) {
     CK(sc->pool_sh_o.alloc(cap * 16));
     CK(sc->pool_sh_d.alloc(cap * 16));
     CK(sc->pool_ic.alloc(cap * 16 * 6));
+    CK(sc->pool_cls.alloc(cap + 16));
+    CK(sc->pool_alive.alloc(cap + 16));
+    CK(cudaMemsetAsync(sc->pool_cls.p, 0xFF, cap + 16, sc->ctx->stream));
+    CK(cudaMemsetAsync(sc->pool_alive.p, 0xFF, cap + 16, sc->ctx->stream));
+    CK(sc->part_tmp.alloc(((cap + PART_PER_BLOCK - 1) / PART_PER_BLOCK) * SHADE_CLASSES * 4));
     CK(sc->active_a.alloc(cap * 4));
     CK(sc->active_b.alloc(cap * 4));
     CK(sc->queues.alloc(cap * 4 * SHADE_CLASSES));
@@ -323,6 +331,9 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
     }();
     for (int c = 0; c < SHADE_CLASSES; ++c) Q.q[c] = sc->queues.as<uint32_t>() + (size_t)c * sc->pool_cap;
     uint32_t* qcounts = sc->qcounts.as<uint32_t>() + bucket_index * COUNT_SLOTS * SHADE_CLASSES;
+    // slot-ordered lists from the per-slot byte columns (dpartition.cuh)
+    const uint32_t part_nb = (n + PART_PER_BLOCK - 1) / PART_PER_BLOCK;
+    uint32_t* part_tmp = sc->part_tmp.as<uint32_t>();
     for (int w = 0; w < WAVES; ++w) {
         Q.count = qcounts + w * SHADE_CLASSES;
         stamp(ev ? &ev->trace : nullptr, true);
@@ -341,6 +352,14 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
         stamp(ev ? &ev->shade : nullptr, true);
         uint32_t* next_active = act[(w + 1) & 1];
         uint32_t* next_count = counts + w + 1;
+        {
+            // class queues of this wave, in slot order
+            PartLists L{};
+            for (int c = 0; c < SHADE_CLASSES; ++c) L.list[c] = Q.q[c], L.total[c] = Q.count + c;
+            k_part_count<SHADE_CLASSES><<<part_nb, PART_THREADS, 0, st>>>(P.cls, n, part_tmp, part_nb);
+            k_part_scan<SHADE_CLASSES><<<1, 1024, 0, st>>>(part_tmp, part_nb, L);
+            k_part_scatter<SHADE_CLASSES><<<part_nb, PART_THREADS, 0, st>>>(P.cls, n, part_tmp, part_nb, L);
+        }
         k_shade<SHADE_SIMPLE><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
         k_shade<SHADE_EMIT><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
         // surface hits: pick a light (tree walk), sample it + evaluate the closure, then bounce + path state
@@ -350,8 +369,16 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
         k_shade_select<SHADE_GGX><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q);
         k_shade_light<SHADE_GGX><<<light_blocks, PSY_LIGHT_THREADS, 0, st>>>(sc->d, P, b, Q);
         k_shade_bounce<SHADE_GGX><<<bounce_blocks, 256, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
+        {
+            // the next wave's live list, in slot order
+            PartLists L{};
+            L.list[0] = next_active, L.total[0] = next_count;
+            k_part_count<1><<<part_nb, PART_THREADS, 0, st>>>(P.alive, n, part_tmp, part_nb);
+            k_part_scan<1><<<1, 1024, 0, st>>>(part_tmp, part_nb, L);
+            k_part_scatter<1><<<part_nb, PART_THREADS, 0, st>>>(P.alive, n, part_tmp, part_nb, L);
+        }
         stamp(ev ? &ev->shade : nullptr, false);
-        *launches += 9;
+        *launches += 15;
     }
     stamp(ev ? &ev->film : nullptr, true);
     k_film<<<(b.w * b.h + 32 * FILM_WARPS - 1) / (32 * FILM_WARPS), 32 * FILM_WARPS, 0, st>>>(P, b, out, stride, ox, oy,
@@ -888,6 +915,8 @@ int32_t psy_trace_rays(PsyScene* sc, const PsyRay* rays, size_t n, PsyHit* hits,
             sc->trace_scratch.as<uint32_t>());
         k_probe_store<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc->d, drays.as<PsyRay>(), (uint32_t)n, P,
                                                                   dhits.as<PsyHit>(), geo ? dgeo.as<PsyHitGeo>() : nullptr);
+        // the trace kernel left a shading class per slot for a shade stage that does not follow here
+        CK(cudaMemsetAsync(sc->pool_cls.p, 0xFF, n, st));
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(hits, dhits.p, n * sizeof(PsyHit), cudaMemcpyDeviceToHost, st));
