@@ -612,6 +612,19 @@ __global__ void __launch_bounds__(32 * FILM_WARPS) k_film(PathPool P, Bucket b, 
     if (q0 >= n_pix) return;
     const float fspp = (float)b.spp;
     V3 acc = mk3(0, 0, 0);
+    if (b.spp < 16u) {
+        // few samples per pixel: a pixel's samples share one or two sectors anyway, one thread per pixel is fine
+        const uint32_t q = q0 + lane;
+        if (q < n_pix) {
+            for (uint32_t si = 0; si < b.spp; ++si) {
+                const uint32_t slot = q * b.spp + si;
+                const float4 c = P.color[slot];
+                if (samples_out) reinterpret_cast<float4*>(samples_out)[slot] = c;
+                const V3 xyz = xyz_from_spectral(from_f4(c), P.wavelength[slot]);
+                acc = acc + mk3(xyz.x / fspp, xyz.y / fspp, xyz.z / fspp);
+            }
+        }
+    } else
     for (uint32_t s0 = 0; s0 < b.spp; s0 += 32u) {
         const uint32_t si = s0 + lane;
         for (uint32_t j = 0; j < 32u; ++j) {
