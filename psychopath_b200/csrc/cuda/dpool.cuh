@@ -9,28 +9,30 @@
 // kind.  Every iteration the warp picks ONE queue, takes up to 32 rays from it, runs that step for
 // all of them together, and files each ray into the queue of its next step.  Lanes are not tied to
 // rays, so every step kind runs with (nearly) full warps whatever the mix is.  Everything is
-// warp-synchronous: no block barrier, no atomics except the global ray fetch and the shade queues.
+// warp-synchronous: no block barrier, no atomics except the global ray fetch.
 //
 // Per ray the order of node visits, primitive tests and instance entries is exactly that of the
 // reference's stack loop, so hits are bit-identical to k_trace and to the oracle.
 //
-// A step is a chain of dependent memory accesses, and with 16 warps per SM the kernel lives or dies
-// by how many L2 round trips one iteration serialises (profiles/r1_pool_r1j.txt: 3-4 trips, 30 %
-// issue utilisation).  So the state is laid out to make the common steps ONE trip:
-//   * the top of the child-reference stack and a 4-entry window below it are in shared memory; only
-//     deeper entries spill to the global scratch area;
-//   * the ray is kept in BOTH the current assembly's space and the current mesh's space, so leaving a
-//     mesh instance restores nothing;
+// A step is a chain of dependent memory accesses, and with 20 warps per SM the kernel lives or dies
+// by how many L2 round trips one iteration serialises (first version: 3-4 trips, 30 % issue
+// utilisation).  So the state is laid out to make the common steps ONE trip:
+//   * the top of the child-reference stack and a 4-entry ring window below it are in shared memory;
+//     pushes also write through to the global scratch area, which only deeper pops read back;
+//   * the ray is kept in the root assembly's, the current assembly's and the current mesh's space at
+//     once: leaving a mesh instance or a first-level assembly is detected by stack height and
+//     restores nothing from memory (deeper nesting saves / reloads through the scratch area);
 //   * the triangle-vertex base of the current mesh is in the state, so a triangle step loads its
 //     vertices (and the mesh's local->world matrix from scratch) straight away;
-//   * node bounds are loaded together with the child words, before the motion-key test.
+//   * node bounds are fetched together with the child words, before the motion-key test, and through
+//     the texture pipe (the LSU pipe carries everything else).
 #pragma once
 // (included at the end of kernels.cuh: uses PathPool, ShadeQueues, the shading classes and dtrace.cuh)
 
 namespace psyd {
 
 #ifndef PSY_POOL_RAYS
-#define PSY_POOL_RAYS 64
+#define PSY_POOL_RAYS 80
 #endif
 constexpr int POOL_RAYS = PSY_POOL_RAYS;  // rays per warp (multiple of 4, < 256)
 constexpr int POOL_WARPS = 4;             // warps per block
