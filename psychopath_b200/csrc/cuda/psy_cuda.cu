@@ -662,7 +662,7 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
     size_t tv_total = 0;
     for (uint32_t m = 0; m < s->n_meshes; ++m) tv_total += (size_t)s->meshes[m].tri_count * 3 * s->meshes[m].n_keys;
     if (tv_total > 0xFFFFFFFFull) return fail(PSY_ERR_LIMIT, "gathered triangle vertex array exceeds 2^32 entries");
-    std::vector<float4> tri_verts(tv_total);
+    // (the gather itself runs on the GPU after the upload, k_gather_tri_verts; the host only checks the indices)
     {
         size_t o = 0;
         for (uint32_t m = 0; m < s->n_meshes; ++m) {
@@ -673,20 +673,15 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
             dm.vert_base = pm.vert_base;
             dm.has_normals = pm.has_normals;
             dm.pad = 0;
-            uint32_t k = pm.n_keys;
             if ((uint64_t)pm.tri_base + pm.tri_count > s->n_tris) return fail(PSY_ERR_INVALID, "mesh triangle range");
+            if (((uint64_t)pm.vert_base + (uint64_t)pm.vert_count * pm.n_keys) > s->n_vert_keys)
+                return fail(PSY_ERR_INVALID, "mesh vertex range");
             for (uint32_t t = 0; t < pm.tri_count; ++t) {
                 const uint32_t* idx = s->tris + (size_t)(pm.tri_base + t) * 4;
-                for (int j = 0; j < 3; ++j) {
-                    if (idx[j] >= pm.vert_count) return fail(PSY_ERR_INVALID, "triangle vertex index out of range");
-                    for (uint32_t key = 0; key < k; ++key) {
-                        const float* v = s->verts + ((size_t)pm.vert_base + (size_t)idx[j] * k + key) * 3;
-                        float w = 0.0f;
-                        if (j == 0 && key == 0) std::memcpy(&w, &idx[3], 4);
-                        tri_verts[o++] = make_float4(v[0], v[1], v[2], w);
-                    }
-                }
+                if (idx[0] >= pm.vert_count || idx[1] >= pm.vert_count || idx[2] >= pm.vert_count)
+                    return fail(PSY_ERR_INVALID, "triangle vertex index out of range");
             }
+            o += (size_t)pm.tri_count * 3 * pm.n_keys;
         }
     }
     // flattened path records for the trace kernel's instance entry (dscene.cuh PATH_*)
@@ -761,7 +756,6 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
     } while (0)
     UP(nodes, s->nodes, (size_t)s->n_nodes);
     UP(motion, s->motion_bounds, (size_t)s->n_motion_bounds);
-    UP(tri_verts, tri_verts.data(), tri_verts.size());
     UP(tris, s->tris, (size_t)s->n_tris * 4);
     UP(normals, normals4.data(), normals4.size());
     UP(meshes, dmeshes.data(), dmeshes.size());
@@ -790,6 +784,26 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
     UP(world_floats, s->world_floats, (size_t)s->n_world_floats);
     UP(meng, &MENG_SPECTRA[0][0], (size_t)186 * 95);
 #undef UP
+    // Triangle vertices in leaf order, [v0 keys][v1 keys][v2 keys] per triangle, gathered on the device from the
+    // vertex keys and the index tuples: the upload carries each vertex once instead of once per use.
+    DevBuf dverts;
+    {
+        cudaError_t e_ = sc->tri_verts.alloc(tv_total * sizeof(float4));
+        if (e_ == cudaSuccess) e_ = dverts.upload(s->verts, (size_t)s->n_vert_keys * 3, st);
+        if (e_ != cudaSuccess) {
+            delete sc;
+            return fail(PSY_ERR_CUDA, std::string("upload vertices: ") + cudaGetErrorString(e_));
+        }
+        sc->upload_bytes += dverts.bytes;
+        for (uint32_t m = 0; m < s->n_meshes; ++m) {
+            const DMesh& dm = dmeshes[m];
+            const uint64_t items = (uint64_t)dm.tri_count * 3 * dm.n_keys;
+            if (items == 0) continue;
+            k_gather_tri_verts<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(
+                sc->tris.as<uint4>(), dverts.as<float>(), sc->tri_verts.as<float4>(), dm.tri_base, dm.tri_count, dm.n_keys,
+                dm.vert_base, dm.tv_base);
+        }
+    }
     cudaError_t e = cudaStreamSynchronize(st);  // the staging vectors above die at return
     if (e != cudaSuccess) {
         delete sc;
