@@ -618,16 +618,18 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, PathPool P, Bucket b, S
 // pixel p's row in order.
 // out: image with row stride `stride` pixels whose origin is pixel (ox, oy).
 constexpr int FILM_WARPS = 2;
+// `ppw` = pixels per warp (<= 32): buckets of many samples per pixel have few pixels, and 32 pixels per warp would
+// leave most of the GPU idle (128 x 128 pixels at 256 spp = 512 warps); the host picks it so that the grid fills the SMs.
 __global__ void __launch_bounds__(32 * FILM_WARPS) k_film(PathPool P, Bucket b, float* out, uint32_t stride, uint32_t ox,
-                                                         uint32_t oy, float* samples_out) {
+                                                         uint32_t oy, float* samples_out, uint32_t ppw) {
     __shared__ float tile[FILM_WARPS][3][32][33];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t n_pix = b.w * b.h;
-    const uint32_t q0 = (blockIdx.x * FILM_WARPS + warp) * 32u;  // first pixel of this warp's group
+    const uint32_t q0 = (blockIdx.x * FILM_WARPS + warp) * ppw;  // first pixel of this warp's group
     if (q0 >= n_pix) return;
     const float fspp = (float)b.spp;
     V3 acc = mk3(0, 0, 0);
-    if (b.spp < 16u) {
+    if (b.spp < 16u) {  // (ppw == 32 here)
         // few samples per pixel: a pixel's samples share one or two sectors anyway, one thread per pixel is fine
         const uint32_t q = q0 + lane;
         if (q < n_pix) {
@@ -642,7 +644,7 @@ __global__ void __launch_bounds__(32 * FILM_WARPS) k_film(PathPool P, Bucket b, 
     } else
     for (uint32_t s0 = 0; s0 < b.spp; s0 += 32u) {
         const uint32_t si = s0 + lane;
-        for (uint32_t j = 0; j < 32u; ++j) {
+        for (uint32_t j = 0; j < ppw; ++j) {
             const uint32_t q = q0 + j;
             V3 v = mk3(0, 0, 0);
             if (q < n_pix && si < b.spp) {
@@ -656,12 +658,13 @@ __global__ void __launch_bounds__(32 * FILM_WARPS) k_film(PathPool P, Bucket b, 
         }
         __syncwarp();
         const uint32_t n_s = min(32u, b.spp - s0);
-        for (uint32_t s = 0; s < n_s; ++s)
-            acc = acc + mk3(tile[warp][0][lane][s], tile[warp][1][lane][s], tile[warp][2][lane][s]);
+        if (lane < ppw)
+            for (uint32_t s = 0; s < n_s; ++s)
+                acc = acc + mk3(tile[warp][0][lane][s], tile[warp][1][lane][s], tile[warp][2][lane][s]);
         __syncwarp();
     }
     const uint32_t q = q0 + lane;
-    if (out && q < n_pix) {
+    if (out && q < n_pix && lane < ppw) {
         const uint32_t px = b.x + (q % b.w), py = b.y + (q / b.w);
         float* o = out + ((size_t)(py - oy) * stride + (px - ox)) * 3;
         o[0] = acc.x, o[1] = acc.y, o[2] = acc.z;

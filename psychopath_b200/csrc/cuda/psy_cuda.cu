@@ -381,8 +381,14 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
         *launches += 15;
     }
     stamp(ev ? &ev->film : nullptr, true);
-    k_film<<<(b.w * b.h + 32 * FILM_WARPS - 1) / (32 * FILM_WARPS), 32 * FILM_WARPS, 0, st>>>(P, b, out, stride, ox, oy,
-                                                                                              samples_out);
+    {
+        // pixels per warp: as many as still give every SM a few warps
+        const uint32_t n_pix = b.w * b.h;
+        uint32_t ppw = 32;
+        while (b.spp >= 16u && ppw > 2u && n_pix / ppw < (uint32_t)sms * 16u) ppw >>= 1;
+        const uint32_t per_block = ppw * FILM_WARPS;
+        k_film<<<(n_pix + per_block - 1) / per_block, 32 * FILM_WARPS, 0, st>>>(P, b, out, stride, ox, oy, samples_out, ppw);
+    }
     stamp(ev ? &ev->film : nullptr, false);
     *launches += 1;
     CK(cudaGetLastError());
