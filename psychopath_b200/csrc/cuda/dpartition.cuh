@@ -3,7 +3,7 @@
 // The trace kernel finishes rays in an arbitrary order, and appending them to the shading queues (and the
 // survivors of shading to the next wave's live list) in completion order interleaves the samples of ~3000
 // different pixels: the shade kernels then read their 16 B pool columns from scattered slots, and the next wave's
-// pools of 64 rays come from 64 different places of the image.  Measured with the lists sorted by slot (radix
+// pools of 80 rays come from 80 different places of the image.  Measured with the lists sorted by slot (radix
 // sort, experiment): shade stage -15 %, trace -3 % (profiles/README.md).
 //
 // So the kernels only write one byte per slot (the ray's shading class / "path continues"), and these three

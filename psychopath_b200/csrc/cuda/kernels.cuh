@@ -1,11 +1,14 @@
 // kernels.cuh — the wavefront stages.  One path owns one slot of the SoA path pool; every wave
 // traces exactly one ray per live path (camera/bounce ray or shadow ray), like the reference's
-// wave loop (src/renderer.rs:279-297), and the live list is compacted with warp ballots.
+// wave loop (src/renderer.rs:279-297).  The kernels mark slots with one byte; the class queues and
+// the next wave's live list are built from those bytes in slot order (dpartition.cuh).
 //
-//   k_generate  <- renderer.rs:241-275  (sampler, pixel filter, LightPath::new, Camera::generate_ray)
-//   k_trace     <- Tracer::trace        (src/tracer.rs:34-37; dtrace.cuh)
-//   k_shade     <- LightPath::next      (renderer.rs:449-691)
-//   k_film      <- renderer.rs:299-310  (XYZ::from_spectral_sample / spp, summed per pixel)
+//   k_generate      <- renderer.rs:241-275  (sampler, pixel filter, LightPath::new, Camera::generate_ray)
+//   k_trace_pool    <- Tracer::trace        (src/tracer.rs:34-37; dpool.cuh — the production trace kernel)
+//   k_trace         <- the same traversal with one ray per lane (dtraverse.cuh): counting build, A/B partner
+//   k_shade<SIMPLE/EMIT>, k_shade_select / _light / _bounce<LAMBERT/GGX>
+//                   <- LightPath::next      (renderer.rs:449-691)
+//   k_film          <- renderer.rs:299-310  (XYZ::from_spectral_sample / spp, summed per pixel)
 #pragma once
 #include <math_constants.h>
 

@@ -27,6 +27,11 @@ def make_scene(name):
     elif name == "instanced":
         s = api.Scene.synth_instanced(asset_quads=24, n_assets=3, n_clusters=9, inst_per_cluster=5,
                                       lights_per_cluster=4, cluster_xform_keys=2, res=(96, 54), spp=4, seed=4)
+    elif name == "clusters":
+        # the bench scene's structure at a size the oracle handles: 30 moving clusters x (8 instances of 4 assets
+        # + 6 sphere / rectangle lights), nested light trees
+        s = api.Scene.synth_instanced(asset_quads=60, n_assets=4, n_clusters=30, inst_per_cluster=8,
+                                      lights_per_cluster=6, cluster_xform_keys=2, res=(96, 54), spp=4, seed=5)
     elif name == "deep_instanced":
         # 20k-triangle assets: BVH4 stacks deeper than the trace kernel's shared-memory stack window
         s = api.Scene.synth_instanced(asset_quads=100, n_assets=2, n_clusters=6, inst_per_cluster=4,
@@ -38,7 +43,7 @@ def make_scene(name):
     return s
 
 
-SCENES = ["cornell", "cube_dof_motion", "fixture", "nested", "instanced", "grid_motion", "deep_instanced"]
+SCENES = ["cornell", "cube_dof_motion", "fixture", "nested", "instanced", "clusters", "grid_motion", "deep_instanced"]
 
 
 def probe_rays(scene, n_random=20000, seed=123):
