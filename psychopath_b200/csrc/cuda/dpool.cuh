@@ -285,27 +285,29 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 const uint32_t ref = ST(PF_TOP, r);
                 const uint4* np = S.nodes + (size_t)ref * 8u;
                 // the whole 128-byte node at once (the static bounds are unused, but valid memory, for motion nodes)
-#if PSY_POOL_NODE_TEX
-                // experiment: node fetches through the texture pipe, next to the LSU pipe that carries everything else
-                const int tn = (int)(ref * 8u);
-                const uint4 child = tex1Dfetch<uint4>(S.nodes_tex, tn);
-                const uint4 meta = tex1Dfetch<uint4>(S.nodes_tex, tn + 1);
+                uint4 child, meta;  // meta: traversal_code, n_keys, key_base, n_children
+                float4 bx0, bx1, by0, by1, bz0, bz1;
+                if (S.nodes_tex) {
+                    // node fetches go through the texture pipe, next to the LSU pipe that carries everything else
+                    // (a scene too large for a linear texture has no texture object and takes the other branch)
+                    const int tn = (int)(ref * 8u);
+                    child = tex1Dfetch<uint4>(S.nodes_tex, tn);
+                    meta = tex1Dfetch<uint4>(S.nodes_tex, tn + 1);
 #define PSY_TEXF4(i)                                                                                          \
     ([&] {                                                                                                    \
         const uint4 t = tex1Dfetch<uint4>(S.nodes_tex, tn + (i));                                             \
         return make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w)); \
     }())
-                float4 bx0 = PSY_TEXF4(2), bx1 = PSY_TEXF4(3), by0 = PSY_TEXF4(4), by1 = PSY_TEXF4(5), bz0 = PSY_TEXF4(6),
-                       bz1 = PSY_TEXF4(7);
+                    bx0 = PSY_TEXF4(2), bx1 = PSY_TEXF4(3), by0 = PSY_TEXF4(4), by1 = PSY_TEXF4(5), bz0 = PSY_TEXF4(6),
+                    bz1 = PSY_TEXF4(7);
 #undef PSY_TEXF4
-                (void)np;
-#else
-                const uint4 child = __ldg(np);
-                const uint4 meta = __ldg(np + 1);  // traversal_code, n_keys, key_base, n_children
-                const float4* bp = reinterpret_cast<const float4*>(np + 2);
-                float4 bx0 = __ldg(bp), bx1 = __ldg(bp + 1), by0 = __ldg(bp + 2), by1 = __ldg(bp + 3), bz0 = __ldg(bp + 4),
-                       bz1 = __ldg(bp + 5);
-#endif
+                } else {
+                    child = __ldg(np);
+                    meta = __ldg(np + 1);
+                    const float4* bp = reinterpret_cast<const float4*>(np + 2);
+                    bx0 = __ldg(bp), bx1 = __ldg(bp + 1), by0 = __ldg(bp + 2), by1 = __ldg(bp + 3), bz0 = __ldg(bp + 4),
+                    bz1 = __ldg(bp + 5);
+                }
                 flags = ST(PF_FLAGS, r);
                 PSY_LOAD_SP()
                 const bool in_mesh = (flags & RF_IN_MESH) != 0u;
@@ -319,16 +321,17 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                     uint32_t i1;
                     float a2;
                     const bool blend = lerp_slice_keys(meta.y, STF(PF_TIME, r), i1, a2);
+                    const int tk = (int)((meta.z + i1) * 6u);
                     const float4* k0 = S.motion_bounds + (size_t)(meta.z + i1) * 6u;
-                    bx0 = __ldg(k0), bx1 = __ldg(k0 + 1), by0 = __ldg(k0 + 2), by1 = __ldg(k0 + 3), bz0 = __ldg(k0 + 4),
-                    bz1 = __ldg(k0 + 5);
+                    const bool mtex = S.motion_tex != 0ull;
+#define PSY_MB(i) (mtex ? tex1Dfetch<float4>(S.motion_tex, tk + (i)) : __ldg(k0 + (i)))
+                    bx0 = PSY_MB(0), bx1 = PSY_MB(1), by0 = PSY_MB(2), by1 = PSY_MB(3), bz0 = PSY_MB(4), bz1 = PSY_MB(5);
                     if (blend) {
-                        const float4* k1 = k0 + 6;
                         const float ia = 1.0f - a2;
 #define PSY_LERP4(A, B) \
     A = make_float4((A.x * ia) + (B.x * a2), (A.y * ia) + (B.y * a2), (A.z * ia) + (B.z * a2), (A.w * ia) + (B.w * a2))
-                        const float4 c0 = __ldg(k1), c1 = __ldg(k1 + 1), c2 = __ldg(k1 + 2), c3 = __ldg(k1 + 3),
-                                     c4 = __ldg(k1 + 4), c5 = __ldg(k1 + 5);
+                        const float4 c0 = PSY_MB(6), c1 = PSY_MB(7), c2 = PSY_MB(8), c3 = PSY_MB(9), c4 = PSY_MB(10),
+                                     c5 = PSY_MB(11);
                         PSY_LERP4(bx0, c0);
                         PSY_LERP4(bx1, c1);
                         PSY_LERP4(by0, c2);
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                         PSY_LERP4(bz1, c5);
 #undef PSY_LERP4
                     }
+#undef PSY_MB
                 }
                 if (COUNT) cnt.node_visits += 1;
                 const float ADJ = 1.00000024f;

@@ -35,11 +35,17 @@ struct DMesh {
 #ifndef PSY_POOL_NODE_TEX
 #define PSY_POOL_NODE_TEX 1
 #endif
+// The motion-key bounds stay on the LSU pipe: 12 more texture fetches per motion node made BASELINE config 2
+// (every node a motion node) 3 % slower (trace 1271 vs 1230 ms per frame).
+#ifndef PSY_POOL_MOTION_TEX
+#define PSY_POOL_MOTION_TEX 0
+#endif
 
 struct DScene {
     // acceleration structures
     const uint4* nodes;          // PsyBvh4Node as 8 x 16 B
     unsigned long long nodes_tex; // the same buffer as a linear uint4 texture object (PSY_POOL_NODE_TEX)
+    unsigned long long motion_tex; // motion_bounds as a linear float4 texture object (PSY_POOL_MOTION_TEX)
     const float4* motion_bounds; // PsyBBox4 as 6 x float4 per key
     // geometry: per triangle (leaf order) 3*k float4: [v0 keys][v1 keys][v2 keys]; v0-key0 .w = original index
     const float4* tri_verts;

@@ -91,6 +91,7 @@ struct PsyScene {
     std::mutex mu;
     ~PsyScene() {
         if (d.nodes_tex) cudaDestroyTextureObject((cudaTextureObject_t)d.nodes_tex);
+        if (d.motion_tex) cudaDestroyTextureObject((cudaTextureObject_t)d.motion_tex);
         for (auto e : events) cudaEventDestroy(e);
     }
 };
@@ -819,20 +820,41 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
     DScene& d = sc->d;
     d.nodes = sc->nodes.as<uint4>();
     d.nodes_tex = 0;
-#if PSY_POOL_NODE_TEX
+    d.motion_tex = 0;
     {
-        cudaResourceDesc rd{};
-        rd.resType = cudaResourceTypeLinear;
-        rd.res.linear.devPtr = sc->nodes.p;
-        rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
-        rd.res.linear.sizeInBytes = (size_t)s->n_nodes * sizeof(PsyBvh4Node);
+        // Linear texture objects over the node and motion-key arrays, when they fit the device's 1D linear texture
+        // limit (16-byte texels); larger scenes leave them 0 and k_trace_pool loads through the LSU pipe instead.
+        // PSY_NODE_TEX=0 / PSY_MOTION_TEX=0 switch them off for A/B measurements.
+        int max_texels = 0;
+        CK(cudaDeviceGetAttribute(&max_texels, cudaDevAttrMaxTexture1DLinearWidth, ctx->device));
+        auto env_on = [](const char* name) {
+            const char* e = getenv(name);
+            return !(e && e[0] == '0');
+        };
         cudaTextureDesc td{};
         td.readMode = cudaReadModeElementType;
-        cudaTextureObject_t tex = 0;
-        if (s->n_nodes) CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
-        d.nodes_tex = tex;
+        if (PSY_POOL_NODE_TEX && env_on("PSY_NODE_TEX") && s->n_nodes && (uint64_t)s->n_nodes * 8 <= (uint64_t)max_texels) {
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = sc->nodes.p;
+            rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+            rd.res.linear.sizeInBytes = (size_t)s->n_nodes * sizeof(PsyBvh4Node);
+            cudaTextureObject_t tex = 0;
+            CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+            d.nodes_tex = tex;
+        }
+        if (PSY_POOL_MOTION_TEX && env_on("PSY_MOTION_TEX") && s->n_motion_bounds &&
+            (uint64_t)s->n_motion_bounds * 6 <= (uint64_t)max_texels) {
+            cudaResourceDesc md{};
+            md.resType = cudaResourceTypeLinear;
+            md.res.linear.devPtr = sc->motion.p;
+            md.res.linear.desc = cudaCreateChannelDesc<float4>();
+            md.res.linear.sizeInBytes = (size_t)s->n_motion_bounds * sizeof(PsyBBox4);
+            cudaTextureObject_t mtex = 0;
+            CK(cudaCreateTextureObject(&mtex, &md, &td, nullptr));
+            d.motion_tex = mtex;
+        }
     }
-#endif
     d.motion_bounds = sc->motion.as<float4>();
     d.tri_verts = sc->tri_verts.as<float4>();
     d.tris = sc->tris.as<uint4>();
