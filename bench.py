@@ -182,7 +182,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("PSY_BENCH_WORKLOAD", "C5"), choices=sorted(WORKLOADS))
-    ap.add_argument("--pool", type=int, default=4 << 20, help="path-pool size (paths in flight per GPU)")
+    ap.add_argument("--pool", type=int, default=0,
+                    help="path-pool size (paths in flight per GPU); 0 = the library's default: the whole image up to "
+                         "64 Mi paths, at least ~6 buckets per GPU when tiled across GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--counter-spp", type=int, default=8)
     ap.add_argument("--spp", type=int, default=0, help="override spp (profiling runs only; not the headline config)")
@@ -214,6 +216,9 @@ def main():
         kw["spp"] = args.spp
         WORKLOAD_DESC[name] += f" [spp overridden to {args.spp}]"
     spp, seed = kw["spp"], kw["seed"]
+    # what psy_render_image / _shard choose when max_samples_per_bucket is 0 (default_pool in psy_cuda.cu)
+    total_samples = kw["res"][0] * kw["res"][1] * spp
+    pool_paths = args.pool or min(64 << 20, max(2 << 20, total_samples // (6 * world) if world > 1 else total_samples))
     scene, build_s = build_scene(name)
     t0 = time.time()
     r = api.Renderer(scene, device=local_rank)
@@ -369,8 +374,8 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD_DESC[name], "resolution": [rx, ry], "spp": spp, "seed": seed,
-                           "paths_in_flight": args.pool, "parallelism": f"tiles x{world}",
-                           "l2": "working set (path pool %d MB + scene) exceeds the 126 MB L2" % (args.pool * 216 >> 20)},
+                           "paths_in_flight": pool_paths, "parallelism": f"tiles x{world}",
+                           "l2": "working set (path pool %d MB + scene) exceeds the 126 MB L2" % (pool_paths * 390 >> 20)},
                 "msamples_s": msamples, "rays_per_step": rays / args.steps, "samples_per_step": samples_per_step,
                 "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
                 "stage_ms_per_step_rank0": stage, "host_build_s": build_s, "upload_s": upload_s}

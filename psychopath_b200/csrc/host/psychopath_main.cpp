@@ -179,7 +179,9 @@ int main(int argc, char** argv) {
         params.crop_x1 = crop[0], params.crop_y1 = crop[1], params.crop_x2 = crop[2], params.crop_y2 = crop[3];
         // --spb on the reference bounds the paths in flight per thread (default 4096); on the GPU the same
         // knob sizes the device path pool, whose default is much larger.
-        params.max_samples_per_bucket = spb;
+        // (without --spb: 4 Mi-path buckets when Blender displays them as they arrive, else as large as the library
+        // allows — the later waves of small buckets cannot fill the GPU)
+        params.max_samples_per_bucket = spb ? spb : (serialized ? (4u << 20) : (64u << 20));
         params.collect_counters = stats ? 1u : 0u;
         std::vector<float> image((size_t)desc->res_x * desc->res_y * 3);
         PsyStats rs;
