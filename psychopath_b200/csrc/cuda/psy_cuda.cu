@@ -609,9 +609,10 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
         std::vector<int64_t> memo(s->n_assemblies, -1);
         int max_nest = 0;
         uint32_t need = stack_need(s, s->root_assembly, memo, 0, max_nest);
-        if (need > (uint32_t)TRACE_STACK_SIZE)
-            return fail(PSY_ERR_LIMIT, "scene needs a traversal stack of " + std::to_string(need) + " entries, limit is " +
-                                           std::to_string(TRACE_STACK_SIZE));
+        // (+1: k_trace_pool writes the nearest hit child to the stack before taking it back as the new top)
+        if (need + 1 > (uint32_t)TRACE_STACK_SIZE)
+            return fail(PSY_ERR_LIMIT, "scene needs a traversal stack of " + std::to_string(need + 1) +
+                                           " entries, limit is " + std::to_string(TRACE_STACK_SIZE));
         if (max_nest >= TRACE_MAX_NEST) return fail(PSY_ERR_LIMIT, "assembly nesting deeper than TRACE_MAX_NEST");
     }
 
