@@ -339,7 +339,7 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
         stamp(ev ? &ev->trace : nullptr, true);
         // The visit counters (--stats, bench.py's roofline pass) are collected by the one-ray-per-lane kernel:
         // both kernels visit exactly the same nodes / primitives per ray, and the counting build of
-        // k_trace_pool is not used (ptxas 12.9 drops the divergence guards of its warp votes, DESIGN.md §6).
+        // k_trace_pool is not used (ptxas 12.9 drops the divergence guards of its warp votes, DESIGN.md §7).
         if (pool_kernel && !counters)
             k_trace_pool<false><<<sc->pool_trace_blocks, 32 * POOL_WARPS, POOL_SMEM_BYTES, st>>>(
                 sc->d, P, act[w & 1], counts + w, fetch + w, nullptr, Q, sc->trace_scratch.as<uint32_t>());
