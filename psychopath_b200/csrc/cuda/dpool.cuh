@@ -40,6 +40,10 @@ constexpr int POOL_WARPS = 4;             // warps per block
 #define PSY_POOL_MIN_BLOCKS 5
 #endif
 constexpr uint32_t POOL_WIN = 4;  // stack entries below the top that stay in shared memory
+#ifndef PSY_POOL_RECYCLE
+#define PSY_POOL_RECYCLE 24  // finished rays / free slots that trigger their recycling (trace ms per C5 frame at
+                             // 16 spp: 8 -> 377, 16 -> 362, 24 -> 354, 32 -> 378)
+#endif
 
 enum PoolQueue { Q_NODE = 0, Q_TRI = 1, Q_INST = 2, Q_DONE = 3, Q_FREE = 4, Q_LIGHT = 5, Q_COUNT = 6 };
 
@@ -180,17 +184,21 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
 
     for (;;) {
         // ---- pick the step kind of this iteration (warp-uniform)
-        // Finished rays and free slots are recycled as soon as half a warp of them has gathered; otherwise the
+        // Finished rays and free slots are recycled as soon as PSY_POOL_RECYCLE of them have gathered; otherwise the
         // fullest of the four work queues runs (ties: triangle > instance > light > node).
         uint32_t k;
         {
             const uint32_t n_done = QLEN(Q_DONE), n_free = QLEN(Q_FREE);
-            const uint32_t key_node = min(QLEN(Q_NODE), 32u) * 8u + 0u, key_light = min(QLEN(Q_LIGHT), 32u) * 8u + 1u,
+#ifndef PSY_POOL_NODE_BIAS
+#define PSY_POOL_NODE_BIAS 0
+#endif
+            const uint32_t key_node = QLEN(Q_NODE) ? (uint32_t)max((int)min(QLEN(Q_NODE), 32u) + PSY_POOL_NODE_BIAS, 1) * 8u : 0u,
+                           key_light = min(QLEN(Q_LIGHT), 32u) * 8u + 1u,
                            key_inst = min(QLEN(Q_INST), 32u) * 8u + 2u, key_tri = min(QLEN(Q_TRI), 32u) * 8u + 3u;
             const uint32_t best = max(max(key_node, key_light), max(key_inst, key_tri));
-            if (n_done >= 16u) {
+            if (n_done >= (uint32_t)PSY_POOL_RECYCLE) {
                 k = Q_DONE;
-            } else if (!exhausted && n_free >= 16u) {
+            } else if (!exhausted && n_free >= (uint32_t)PSY_POOL_RECYCLE) {
                 k = Q_FREE;
             } else if (best >= 8u) {
                 k = (0x1250u >> ((best & 7u) * 4u)) & 15u;  // tie-break rank -> queue: 0 node, 1 light, 2 inst, 3 tri
