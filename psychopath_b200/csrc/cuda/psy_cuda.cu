@@ -36,6 +36,18 @@ int32_t fail(int32_t code, const std::string& msg) {
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr, o.bytes = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            if (p) cudaFree(p);
+            p = o.p, bytes = o.bytes;
+            o.p = nullptr, o.bytes = 0;
+        }
+        return *this;
+    }
     ~DevBuf() {
         if (p) cudaFree(p);
     }
@@ -60,10 +72,21 @@ struct DevBuf {
 
 }  // namespace
 
+// The path pool and the trace scratch area do not depend on the scene (25 GB at the default size): a destroyed
+// scene leaves them with its context, and the next scene that needs a pool no larger takes them over instead of
+// allocating — rendering frame after frame (Blender, bench.py's end-to-end arm) pays for cudaMalloc / cudaFree once.
+struct PoolCache {
+    std::vector<DevBuf> bufs;
+    size_t cap = 0;
+    uint32_t trace_blocks = 0;
+};
+
 struct PsyContext {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    std::mutex cache_mu;
+    PoolCache cache;
 };
 
 struct PsyScene {
@@ -222,8 +245,49 @@ PathPool make_pool(PsyScene* sc) {
     return P;
 }
 
+// the scene-independent buffers, in a fixed order (PoolCache::bufs uses the same order)
+std::vector<DevBuf*> pool_buffers(PsyScene* sc) {
+    return {&sc->pool_ray_o, &sc->pool_ray_d, &sc->pool_flags, &sc->pool_sseed, &sc->pool_wl, &sc->pool_cpdf,
+            &sc->pool_nb_o, &sc->pool_nb_d, &sc->pool_next_atten, &sc->pool_light_atten, &sc->pool_pending,
+            &sc->pool_color, &sc->pool_hits, &sc->pool_light_pick, &sc->pool_light_uv, &sc->pool_sh_o, &sc->pool_sh_d,
+            &sc->pool_ic, &sc->pool_cls, &sc->pool_alive, &sc->part_tmp, &sc->active_a, &sc->active_b, &sc->queues,
+            &sc->trace_scratch};
+}
+
+// psy_scene_destroy: leave the pool with the context if it is the larger one
+void donate_pool(PsyScene* sc) {
+    if (sc->pool_cap == 0) return;
+    PsyContext* ctx = sc->ctx;
+    std::lock_guard<std::mutex> g(ctx->cache_mu);
+    if (sc->pool_cap <= ctx->cache.cap) return;
+    std::vector<DevBuf*> mine = pool_buffers(sc);
+    ctx->cache.bufs.clear();  // frees a smaller cached pool
+    ctx->cache.bufs.resize(mine.size());
+    for (size_t i = 0; i < mine.size(); ++i) ctx->cache.bufs[i] = std::move(*mine[i]);
+    ctx->cache.cap = sc->pool_cap;
+    ctx->cache.trace_blocks = sc->pool_trace_blocks;
+    sc->pool_cap = 0;
+}
+
 int32_t ensure_pool(PsyScene* sc, size_t n) {
     if (n <= sc->pool_cap) return PSY_OK;
+    if (sc->pool_cap == 0) {
+        // a pool left behind by an earlier scene of this context?
+        PsyContext* ctx = sc->ctx;
+        std::lock_guard<std::mutex> g(ctx->cache_mu);
+        if (ctx->cache.cap >= n) {
+            std::vector<DevBuf*> mine = pool_buffers(sc);
+            for (size_t i = 0; i < mine.size(); ++i) *mine[i] = std::move(ctx->cache.bufs[i]);
+            sc->pool_cap = ctx->cache.cap;
+            sc->pool_trace_blocks = ctx->cache.trace_blocks;
+            ctx->cache.bufs.clear();
+            ctx->cache.cap = 0;
+            // the byte columns are clean after a completed render; make sure after an aborted one
+            CK(cudaMemsetAsync(sc->pool_cls.p, 0xFF, sc->pool_cap + 16, ctx->stream));
+            CK(cudaMemsetAsync(sc->pool_alive.p, 0xFF, sc->pool_cap + 16, ctx->stream));
+            return PSY_OK;
+        }
+    }
     size_t cap = n;
     CK(sc->pool_ray_o.alloc(cap * 16));
     CK(sc->pool_ray_d.alloc(cap * 16));
@@ -919,6 +983,7 @@ int32_t psy_scene_destroy(PsyScene* scene) {
     if (!scene) return PSY_OK;
     cudaSetDevice(scene->ctx->device);
     cudaStreamSynchronize(scene->ctx->stream);
+    donate_pool(scene);
     delete scene;
     return PSY_OK;
 }
