@@ -309,7 +309,9 @@ typedef struct PsyRenderParams {
     uint32_t spp;                 /* 0 = scene's */
     uint32_t seed_override_enabled;
     uint32_t seed;
-    uint32_t max_samples_per_bucket; /* `--spb`; on the GPU this is the path-pool size; 0 = default */
+    uint32_t max_samples_per_bucket; /* `--spb`; on the GPU this is the path-pool size (paths in flight, ~390 B each);
+                                        0 = default: the whole image up to 64 Mi paths, ~6 buckets per GPU when the
+                                        image is tiled across GPUs, 4 Mi when buckets are streamed to a callback */
     uint32_t collect_counters;    /* 1 = run the counters build of the trace kernel */
     uint32_t device_resident_only; /* 1 = leave the image on the device, skip the D2H copy (bench `value`) */
 } PsyRenderParams;
