@@ -1143,8 +1143,26 @@ int32_t psy_render_image_shard(PsyScene* sc, const PsyRenderParams* p, uint32_t 
     std::vector<Bucket> all, mine;
     int32_t rc = image_jobs(sc, p, all, world);
     if (rc) return rc;
-    for (size_t j = 0; j < all.size(); ++j)
-        if (j % world == rank) mine.push_back(all[j]);
+    // Deal the buckets so that every rank gets about the same number of samples: largest first, each to the rank with
+    // the least so far (the buckets at the image border are partial; plain round-robin left ranks idle at 8 GPUs).
+    // Every rank computes the same assignment; a rank renders its buckets in Hilbert order.
+    {
+        std::vector<size_t> order(all.size());
+        for (size_t j = 0; j < all.size(); ++j) order[j] = j;
+        auto samples = [&](size_t j) { return (uint64_t)all[j].w * all[j].h * all[j].spp; };
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return samples(a) > samples(b); });
+        std::vector<uint64_t> load(world, 0);
+        std::vector<size_t> my_idx;
+        for (size_t j : order) {
+            uint32_t r = 0;
+            for (uint32_t k = 1; k < world; ++k)
+                if (load[k] < load[r]) r = k;
+            load[r] += samples(j);
+            if (r == rank) my_idx.push_back(j);
+        }
+        std::sort(my_idx.begin(), my_idx.end());
+        for (size_t j : my_idx) mine.push_back(all[j]);
+    }
     if (sc->image.p) CK(cudaMemsetAsync(sc->image.p, 0, sc->image.bytes, sc->ctx->stream));
     return render_buckets(sc, mine, p && p->collect_counters, stats, nullptr, nullptr, nullptr);
 }

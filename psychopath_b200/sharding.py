@@ -2,7 +2,8 @@
 tiles dealt to the ranks, one collective at the end.
 
 The image partitions into the Hilbert-ordered bucket list of Renderer::render (src/renderer.rs:138-180);
-bucket j goes to rank j % world (psy_render_image_shard does the same split on the device side).  Ranks
+the buckets are dealt to the ranks by size so that every rank gets about the same number of samples
+(psy_render_image_shard computes the same assignment on the device side).  Ranks
 render into zero-initialised full-size images, so the gather to rank 0 is a single SUM reduce of
 disjoint tiles (NCCL on GPUs; gloo in the CPU tests).
 """
@@ -28,7 +29,17 @@ def bucket_list(width, height, bucket_w, start=(0, 0)):
 
 
 def buckets_for_rank(buckets, rank, world):
-    return [b for j, b in enumerate(buckets) if j % world == rank]
+    """The buckets of one rank: largest first, each to the rank with the fewest pixels so far (ties: lowest rank),
+    returned in Hilbert order — the assignment psy_render_image_shard computes on the device side."""
+    order = sorted(range(len(buckets)), key=lambda j: -(buckets[j][2] * buckets[j][3]))  # stable, like std::stable_sort
+    load = [0] * world
+    mine = []
+    for j in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        load[r] += buckets[j][2] * buckets[j][3]
+        if r == rank:
+            mine.append(j)
+    return [buckets[j] for j in sorted(mine)]
 
 
 def gather_image(image, dst=0, group=None):
