@@ -50,6 +50,25 @@ def _worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
+def test_bucket_assignment_is_a_balanced_partition():
+    """Every bucket goes to exactly one rank, each rank keeps Hilbert order, and no rank carries more than one
+    bucket's worth of pixels above the mean (the longest-processing-time-first bound)."""
+    sys.path.insert(0, REPO)
+    from psychopath_b200 import sharding
+    for (rx, ry, bw) in ((3840, 2160, 412), (1920, 1080, 300), (96, 64, 11)):
+        buckets = sharding.bucket_list(rx, ry, bw)
+        assert sum(w * h for (_, _, w, h) in buckets) == rx * ry
+        for world in (1, 2, 3, 8):
+            shares = [sharding.buckets_for_rank(buckets, r, world) for r in range(world)]
+            assert sorted(b for s in shares for b in s) == sorted(buckets)
+            for s in shares:
+                idx = [buckets.index(b) for b in s]
+                assert idx == sorted(idx)
+            loads = [sum(w * h for (_, _, w, h) in s) for s in shares]
+            biggest = max(w * h for (_, _, w, h) in buckets)
+            assert max(loads) <= rx * ry / world + biggest
+
+
 def test_two_rank_tile_gather(tmp_path):
     out = str(tmp_path / "img.npy")
     port = _free_port()
