@@ -6,15 +6,16 @@ Workload (config C5): the synthetic hierarchical-instancing scene (100 cluster s
 through nested light trees, moving cluster instances with 2 transform keys) at 3840x2160, 256 spp.
 
 A step = one full render of that image.  With N > 1 ranks (torchrun, one process per GPU) the
-Hilbert-ordered tiles are dealt round-robin to the ranks (scene replicated per GPU, no exchange while
+Hilbert-ordered tiles are dealt to the ranks by sample count (scene replicated per GPU, no exchange while
 rendering) and the disjoint device tiles are summed onto rank 0 with one NCCL reduce per step;
 total work is fixed, so scaling is "strong".
 
   value     whole-job Mrays/s, scene resident in HBM, image left on the device
   e2e       the same metric through the C ABI with host buffers: every step uploads the scene
             description (H2D) and fetches the finished image (D2H)
-  roofline  k_trace (the dominant kernel): algorithmic bytes of SURVEY.md 8(d)'s formula, with visit
-            counts measured by the counters build, over the CUDA-event time of the trace launches
+  roofline  k_trace_pool (the dominant kernel): algorithmic bytes of SURVEY.md 8(d)'s formula, with visit
+            counts measured by the counting trace kernel, over the CUDA-event time of the trace launches;
+            traffic = the kernel's measured DRAM bytes per ray (profiles/r1_trace_dram.json) x rays per launch
   cpu_baseline / --impl reference: the CPU oracle (restated reference path; the Rust reference cannot be
             built here) on the host cores, on a bounded sample of the same workload.
 """
