@@ -61,6 +61,26 @@ def test_no_cpu_fallback():
         api.Renderer(scene)
 
 
+def test_cli_without_a_gpu_fails_loudly():
+    """bin/psychopath parses its arguments like src/main.rs and, with no CUDA device, stops with the library's
+    error instead of rendering on the CPU."""
+    import subprocess
+    import torch
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(repo, "bin", "psychopath")
+    out = subprocess.run([exe, "--dev"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "PsyBvh4Node size: 128 bytes" in out.stdout
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode != 0 and "--input" in out.stderr
+    out = subprocess.run([exe, "-i", "x.psy", "--crop", "5", "1", "2", "3"], capture_output=True, text=True, timeout=60)
+    assert out.returncode != 0 and "X1 must be less than or equal to X2" in out.stderr
+    if torch.cuda.is_available():
+        return
+    scene = os.path.join(repo, "tests", "golden", "cube.psy")
+    out = subprocess.run([exe, "-i", scene], capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0 and "no CPU fallback" in out.stderr
+
+
 def test_product_package_never_touches_the_oracle():
     pkg = os.path.join(REPO, "psychopath_b200")
     for root, _, files in os.walk(pkg):
