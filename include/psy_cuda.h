@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PSY_ABI_VERSION 1
+#define PSY_ABI_VERSION 2
 
 /* status codes */
 #define PSY_OK 0
@@ -314,6 +314,10 @@ typedef struct PsyRenderParams {
                                         image is tiled across GPUs, 4 Mi when buckets are streamed to a callback */
     uint32_t collect_counters;    /* 1 = run the counters build of the trace kernel */
     uint32_t device_resident_only; /* 1 = leave the image on the device, skip the D2H copy (bench `value`) */
+    uint32_t strict_film_order;   /* 1 = add every bucket's samples to the film in the reference's path order after its
+                                     swap compaction (src/renderer.rs:286-310): the image then depends on the bucket
+                                     list exactly as the reference's does, so max_samples_per_bucket is the reference's
+                                     `--spb` (0 = its default 4096) and a bucket holds at most 65536 paths (src/ray.rs:7) */
 } PsyRenderParams;
 
 typedef void (*psy_bucket_cb)(void* user, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
@@ -324,6 +328,10 @@ typedef struct PsyScene PsyScene;
 
 const char* psy_last_error(void);
 int32_t psy_abi_version(void);
+/* bit 0: the library was built with -DPSY_STRICT=1 (libpsy_cuda_strict.so): sin/cos/acos/asin/log come from
+ * include/psy_detmath.h instead of libdevice, like the oracle's strict mode (parity tests only; ~2x slower shading) */
+#define PSY_BUILD_STRICT_MATH 1u
+uint32_t psy_build_flags(void);
 
 /* device_ids == NULL -> device 0.  One context per process per GPU set. */
 int32_t psy_init(const int* device_ids, int n_devices, PsyContext** out);

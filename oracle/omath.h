@@ -16,8 +16,25 @@
 #include <limits>
 
 #include "../include/psy_cuda.h"
+#include "../include/psy_detmath.h"
 
 namespace orc {
+
+// The eight libm functions of the path.  Default: glibc, as the reference (Rust std) uses.  Strict mode
+// (oracle_set_strict_math): the deterministic functions of include/psy_detmath.h, which the strict build of the
+// CUDA path uses as well — then CPU and GPU compute every sample with the same bits.
+inline bool& strict_math() {
+    static bool on = false;
+    return on;
+}
+inline float m_sinf(float x) { return strict_math() ? psy_det_sinf(x) : std::sin(x); }
+inline float m_cosf(float x) { return strict_math() ? psy_det_cosf(x) : std::cos(x); }
+inline float m_acosf(float x) { return strict_math() ? psy_det_acosf(x) : std::acos(x); }
+inline float m_asinf(float x) { return strict_math() ? psy_det_asinf(x) : std::asin(x); }
+inline double m_sin(double x) { return strict_math() ? psy_det_sin(x) : std::sin(x); }
+inline double m_cos(double x) { return strict_math() ? psy_det_cos(x) : std::cos(x); }
+inline double m_acos(double x) { return strict_math() ? psy_det_acos(x) : std::acos(x); }
+inline double m_log(double x) { return strict_math() ? psy_det_log(x) : std::log(x); }
 
 struct V3 {
     float x, y, z;

@@ -678,6 +678,7 @@ struct Tracer {
 //------------------------------------------------------------------------------------------------
 // Light sampling
 
+static bool g_dbg_on = false;
 struct LightSample {
     int kind = 0;  // 0 none, 1 distant, 2 surface
     V4 color{};
@@ -717,6 +718,9 @@ struct LightSampler {
             float r2 = length2(bmax - bmin) * 0.25f;
             float inv_surface_area = 1.0f / r2;
             float approx_contrib = closure_estimate_sphere(sc, inc, dd, r2, nor, nor_g);
+            if (g_dbg_on)
+                std::fprintf(stderr, "[oracle dbg]     child energy %.9g r2 %.9g dd (%.9g %.9g %.9g) contrib %.9g\n", (double)nd.energy,
+                             (double)r2, (double)dd.x, (double)dd.y, (double)dd.z, (double)approx_contrib);
             return nd.energy * inv_surface_area * approx_contrib;
         };
         const PsyLightNode* node = d.light_nodes + a.light_root;
@@ -789,7 +793,7 @@ struct LightSampler {
             double cos_a = ddd <= 0.0 ? sin_theta_max : ((dd / radius) * sin_theta2) + (cos_theta * std::sqrt(ddd));
             double sin_a = std::sqrt(rmax(1.0 - (cos_a * cos_a), 0.0));
             double phi = (double)v * 2.0 * PI_64;
-            V3 s2 = mk((float)(std::cos(phi) * sin_a * radius), (float)(std::sin(phi) * sin_a * radius),
+            V3 s2 = mk((float)(m_cos(phi) * sin_a * radius), (float)(m_sin(phi) * sin_a * radius),
                        (float)(dd - (cos_a * radius)));
             V3 sample_vec = ((x * s2.x) + (y * s2.y)) + (z * s2.z);
             V3 normal = normalized(arr + sample_vec);
@@ -954,10 +958,10 @@ struct LightSampler {
             double radius = (double)lerp_slice(d.world_floats + l.radii_base, l.n_radii, time);
             V3 direction = lerp_slice_fn<V3>(l.n_dirs, time, [&](size_t k) { return b3(d.world_floats + l.dir_base + 3 * k); });
             PsyColor col = lerp_slice(d.light_colors + l.color_base, l.n_colors, time);
-            double solid_angle_inv = 1.0 / (2.0 * PI_64 * (1.0 - std::cos(radius)));
+            double solid_angle_inv = 1.0 / (2.0 * PI_64 * (1.0 - m_cos(radius)));
             V3 z = -normalized(direction), x2, y2;
             coordinate_system_from_vector(z, x2, y2);
-            double cos_theta_max = std::cos(radius);
+            double cos_theta_max = m_cos(radius);
             V3 sample = normalized(uniform_sample_cone(u, v, cos_theta_max));
             out.kind = 1;
             out.color = color_to_spectral(col, wl) * (float)solid_angle_inv;
@@ -1001,6 +1005,18 @@ static Ray camera_ray(const PsySceneDesc& d, float x, float y, float time, float
     return r;
 }
 
+// Debug trace of one sample's path events (oracle_set_debug): prints every quantity LightPath::next derives.
+static uint32_t g_dbg_px = 0xFFFFFFFFu, g_dbg_py = 0, g_dbg_si = 0;
+#define ORC_DBG(...)                                                               \
+    do {                                                                           \
+        if (px == g_dbg_px && py == g_dbg_py && sample_number == g_dbg_si) {       \
+            std::fprintf(stderr, "[oracle dbg] " __VA_ARGS__);                     \
+            std::fprintf(stderr, "\n");                                            \
+        }                                                                          \
+    } while (0)
+#define ORC_V4(q_) (double)(q_).v[0], (double)(q_).v[1], (double)(q_).v[2], (double)(q_).v[3]
+#define ORC_V3(q_) (double)(q_).x, (double)(q_).y, (double)(q_).z
+
 enum Event { EV_CAMERA, EV_BOUNCE, EV_SHADOW };
 struct LightPath {
     Event event = EV_CAMERA;
@@ -1028,6 +1044,9 @@ struct LightPath {
 
     // LightPath::next (renderer.rs:449-691)
     bool next(LightSampler& ls, const PsySceneDesc& d, const Isect& isect, Ray& ray) {
+        ORC_DBG("event %d bounce %u isect.kind %d hit_kind %u t %.9g prim %u path %u ray o (%.9g %.9g %.9g) d (%.9g %.9g %.9g) time %.9g wl %.9g",
+                (int)event, bounce_count, (int)isect.kind, isect.hit_kind, (double)isect.t, isect.prim_id, isect.path_id, ORC_V3(ray.orig),
+                ORC_V3(ray.dir), (double)time, (double)wavelength);
         if (event == EV_CAMERA || event == EV_BOUNCE) {
             if (isect.kind == ISECT_HIT) {
                 const Closure& closure = isect.closure;
@@ -1041,13 +1060,21 @@ struct LightPath {
                     }
                     return false;
                 }
+                ORC_DBG("  hit pos (%.9g %.9g %.9g) err %.9g nor (%.9g %.9g %.9g) nor_g (%.9g %.9g %.9g) closure %u atten (%.9g %.9g %.9g %.9g) cpdf %.9g",
+                        ORC_V3(isect.pos), (double)isect.pos_err, ORC_V3(isect.nor), ORC_V3(isect.nor_g), closure.kind,
+                        ORC_V4(light_attenuation), (double)closure_sample_pdf);
                 light_attenuation = light_attenuation / closure_sample_pdf;
 
                 next_lds_sequence();
                 float s4[4];
                 next_lds_samp(s4);
+                g_dbg_on = (px == g_dbg_px && py == g_dbg_py && sample_number == g_dbg_si);
                 LightSample li = ls.sample_scene(s4[0], s4[1], s4[2], s4[3], wavelength, time, isect);
+                g_dbg_on = false;
                 bool found_light = false;
+                ORC_DBG("  light kind %d pdf %.9g sel %.9g color (%.9g %.9g %.9g %.9g) pos (%.9g %.9g %.9g) nor (%.9g %.9g %.9g) dir (%.9g %.9g %.9g) s4 (%.9g %.9g %.9g)",
+                        li.kind, (double)li.pdf, (double)li.selection_pdf, ORC_V4(li.color), ORC_V3(li.pos), ORC_V3(li.nor),
+                        ORC_V3(li.direction), (double)s4[0], (double)s4[1], (double)s4[2]);
                 if (!(li.kind == 0 || li.pdf <= 0.0f || li.selection_pdf <= 0.0f)) {
                     V4 attenuation;
                     float closure_pdf;
@@ -1070,9 +1097,11 @@ struct LightPath {
                     }
                     shadow.time = time;
                     shadow.occlusion = true;
+                    ORC_DBG("  eval atten (%.9g %.9g %.9g %.9g) closure_pdf %.9g", ORC_V4(attenuation), (double)closure_pdf);
                     if (!(max_element(attenuation) <= 0.0f)) {
                         float light_mis_pdf = power_heuristic(li.pdf, closure_pdf);
                         pending_color_addition = ((li.color * attenuation) * light_attenuation) / (light_mis_pdf * li.selection_pdf);
+                        ORC_DBG("  pending (%.9g %.9g %.9g %.9g) mis %.9g", ORC_V4(pending_color_addition), (double)light_mis_pdf);
                         ray = shadow;
                         found_light = true;
                     }
@@ -1088,6 +1117,7 @@ struct LightPath {
                     V4 filter;
                     float pdf;
                     closure_sample(closure, isect.incoming, isect.nor, isect.nor_g, b4[0], b4[1], wavelength, dir, filter, pdf);
+                    ORC_DBG("  bounce dir (%.9g %.9g %.9g) filter (%.9g %.9g %.9g %.9g) pdf %.9g", ORC_V3(dir), ORC_V4(filter), (double)pdf);
                     if ((pdf > 0.0f) && (max_element(filter) > 0.0f)) {
                         next_attenuation_fac = filter;
                         closure_sample_pdf = pdf;
@@ -1435,6 +1465,14 @@ int oracle_camera_rays(const PsySceneDesc* d, uint32_t x0, uint32_t y0, uint32_t
 }
 
 //---- unit-level entry points used to pin the restatement against the reference's own tests -------
+void oracle_set_strict_math(int on) { strict_math() = on != 0; }
+double oracle_det_f64(int fn, double x) {
+    return fn == 0 ? psy_det_sin(x) : fn == 1 ? psy_det_cos(x) : fn == 2 ? psy_det_acos(x) : fn == 3 ? psy_det_asin(x) : psy_det_log(x);
+}
+float oracle_det_f32(int fn, float x) {
+    return fn == 0 ? psy_det_sinf(x) : fn == 1 ? psy_det_cosf(x) : fn == 2 ? psy_det_acosf(x) : psy_det_asinf(x);
+}
+void oracle_set_debug(uint32_t px, uint32_t py, uint32_t si) { g_dbg_px = px, g_dbg_py = py, g_dbg_si = si; }
 uint32_t oracle_hash_u32(uint32_t n, uint32_t seed) { return hash_u32(n, seed); }
 float oracle_golden_ratio_sample(uint32_t i, uint32_t scramble) { return golden_ratio_sample(i, scramble); }
 void oracle_get_sample_4d(uint32_t i, uint32_t ds, uint32_t px, uint32_t py, uint32_t seed, float* out) {

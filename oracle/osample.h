@@ -9,7 +9,7 @@
 //     index-shuffled Sobol.  Restated from the crate's published design: shuffle the bit-reversed
 //     index with a Laine-Karras style hash seeded by hash(seed); XOR the bit-reversed Joe-Kuo
 //     direction vectors selected by the top 16 bits; Owen-scramble each lane with a per-lane
-//     hashed seed; reverse the bits back; take the top 24 bits as a float in [0,1).  The CUDA path
+//     hashed seed; reverse the bits back; put the top 23 bits into the mantissa of a float in [1,2) and subtract 1.  The CUDA path
 //     uses exactly the same integer recipe, so "identical sample sequences" holds between oracle
 //     and GPU; whether every constant equals upstream's cannot be checked offline.
 //   * fastapprox 0.3.0 (Cargo.lock) — fast::pow2 / fast::exp, restated from the published
@@ -81,7 +81,11 @@ inline void sobol_sample_4d(uint32_t index, uint32_t dimension_set, uint32_t see
             lane_seed ^= lane_seed >> 16;
         }
         uint32_t v = reverse_bits(sb_lk_scramble(sob[l], lane_seed));
-        out[l] = (float)(v >> 8) * (1.0f / 16777216.0f);
+        // sobol_burley's to_norm_floats: the top 23 bits become the mantissa of a float in [1, 2), minus 1
+        const uint32_t fb = (v >> 9) | 0x3f800000u;
+        float f;
+        std::memcpy(&f, &fb, 4);
+        out[l] = f - 1.0f;
     }
 }
 
@@ -115,7 +119,7 @@ inline float probit(float nf, float width) {
     const double N_LOW = 0.02425, N_HIGH = 1.0 - N_LOW;
     double x;
     if (0.0 < n && n < N_LOW) {
-        double q = std::sqrt(-2.0 * std::log(n));
+        double q = std::sqrt(-2.0 * m_log(n));
         x = (((((C1 * q + C2) * q + C3) * q + C4) * q + C5) * q + C6) / ((((D1 * q + D2) * q + D3) * q + D4) * q + 1.0);
     } else if (n <= N_HIGH) {
         // also taken for n <= 0: the reference's match arms are tried in this order
@@ -124,7 +128,7 @@ inline float probit(float nf, float width) {
         x = (((((A1 * r + A2) * r + A3) * r + A4) * r + A5) * r + A6) * q /
             (((((B1 * r + B2) * r + B3) * r + B4) * r + B5) * r + 1.0);
     } else if (n < 1.0) {
-        double q = std::sqrt(-2.0 * std::log(1.0 - n));
+        double q = std::sqrt(-2.0 * m_log(1.0 - n));
         x = -(((((C1 * q + C2) * q + C3) * q + C4) * q + C5) * q + C6) / ((((D1 * q + D2) * q + D3) * q + D4) * q + 1.0);
     } else if (n == 1.0) {
         x = std::numeric_limits<double>::infinity();
@@ -164,8 +168,8 @@ inline void square_to_circle(float x, float y, float& ox, float& oy) {
         radius = -y;
         angle = QPI * (6.0f - (x / y));
     }
-    ox = radius * std::cos(angle);
-    oy = radius * std::sin(angle);
+    ox = radius * m_cosf(angle);
+    oy = radius * m_sinf(angle);
 }
 inline V3 cosine_sample_hemisphere(float u, float v) {
     float a, b;
@@ -178,14 +182,14 @@ inline V3 uniform_sample_sphere(float u, float v) {
     float z = 1.0f - (2.0f * u);
     float r = std::sqrt(rmax(1.0f - (z * z), 0.0f));
     float phi = 2.0f * PI_32 * v;
-    return mk(r * std::cos(phi), r * std::sin(phi), z);
+    return mk(r * m_cosf(phi), r * m_sinf(phi), z);
 }
 const double PI_64 = 3.14159265358979323846;
 inline V3 uniform_sample_cone(float u, float v, double cos_theta_max) {
     double cos_theta = (1.0 - (double)u) + ((double)u * cos_theta_max);
     double sin_theta = std::sqrt(1.0 - (cos_theta * cos_theta));
     double phi = (double)v * 2.0 * PI_64;
-    return mk((float)(std::cos(phi) * sin_theta), (float)(std::sin(phi) * sin_theta), (float)cos_theta);
+    return mk((float)(m_cos(phi) * sin_theta), (float)(m_sin(phi) * sin_theta), (float)cos_theta);
 }
 inline double uniform_sample_cone_pdf(double cos_theta_max) { return 1.0 / (2.0 * PI_64 * (1.0 - cos_theta_max)); }
 inline V3 uniform_sample_triangle(V3 va, V3 vb, V3 vc, float i, float j) {
@@ -209,7 +213,7 @@ inline float spherical_triangle_solid_angle(V3 va, V3 vb, V3 vc) {
     double cos_va = rmin(rmax((cos_a - (cos_b * cos_c)) / (sin_b * sin_c), -1.0), 1.0);
     double cos_vb = rmin(rmax((cos_b - (cos_c * cos_a)) / (sin_c * sin_a), -1.0), 1.0);
     double cos_vc = rmin(rmax((cos_c - (cos_a * cos_b)) / (sin_a * sin_b), -1.0), 1.0);
-    double ang_va = std::acos(cos_va), ang_vb = std::acos(cos_vb), ang_vc = std::acos(cos_vc);
+    double ang_va = m_acos(cos_va), ang_vb = m_acos(cos_vb), ang_vc = m_acos(cos_vc);
     return (float)(ang_va + ang_vb + ang_vc - PI_64);
 }
 
@@ -226,11 +230,11 @@ inline V3 uniform_sample_spherical_triangle(V3 va, V3 vb, V3 vc, float i, float 
     double cos_vb = rmin(rmax((cos_b - (cos_c * cos_a)) / (sin_c * sin_a), -1.0), 1.0);
     double cos_vc = rmin(rmax((cos_c - (cos_a * cos_b)) / (sin_a * sin_b), -1.0), 1.0);
     double sin_va = std::sqrt(1.0 - (cos_va * cos_va));
-    double ang_va = std::acos(cos_va), ang_vb = std::acos(cos_vb), ang_vc = std::acos(cos_vc);
+    double ang_va = m_acos(cos_va), ang_vb = m_acos(cos_vb), ang_vc = m_acos(cos_vc);
     double area = ang_va + ang_vb + ang_vc - PI_64;
     double area_2 = area * (double)i;
-    double s = std::sin(area_2 - ang_va);
-    double t = std::cos(area_2 - ang_va);
+    double s = m_sin(area_2 - ang_va);
+    double t = m_cos(area_2 - ang_va);
     double u = t - cos_va;
     double v = s + (sin_va * cos_c);
     double q_top = (((v * t) - (u * s)) * cos_va) - v;

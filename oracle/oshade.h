@@ -293,7 +293,7 @@ inline void closure_sample(const Closure& cl, V3 inc, V3 nor, V3 nor_g, float u,
         float theta_cos = half_theta_sample(u, cl.roughness);
         float theta_sin = std::sqrt(1.0f - (theta_cos * theta_cos));
         float angle = v * PI_32 * 2.0f;
-        V3 half_dir = mk(std::cos(angle) * theta_sin, std::sin(angle) * theta_sin, theta_cos);
+        V3 half_dir = mk(m_cosf(angle) * theta_sin, m_sinf(angle) * theta_sin, theta_cos);
         half_dir = normalized(zup_to_vec(half_dir, nn));
         V3 out = inc - (half_dir * 2.0f * dot(inc, half_dir));
         dir = out;
@@ -317,10 +317,10 @@ inline float sphere_lambert(float nlcos, float rcos) {
     float ysin = rcos / nlsin;
     float ycos2 = 1.0f - (ysin * ysin);
     float ycos = std::sqrt(ycos2);
-    float g = (-2.0f * nlsin * rcos * ycos) + H_PI - std::asin(ysin) + (ysin * ycos);
-    float h = nlcos * ((ycos * std::sqrt(rsin2 - ycos2)) + (rsin2 * std::asin(ycos / rsin)));
-    float nl = std::acos(nlcos);
-    float r = std::acos(rcos);
+    float g = (-2.0f * nlsin * rcos * ycos) + H_PI - m_asinf(ysin) + (ysin * ycos);
+    float h = nlcos * ((ycos * std::sqrt(rsin2 - ycos2)) + (rsin2 * m_asinf(ycos / rsin)));
+    float nl = m_acosf(nlcos);
+    float r = m_acosf(rcos);
     if (nl < (H_PI - r)) return nlcos * rsin2;
     if (nl < H_PI) return (nlcos * rsin2) + g - h;
     if (nl < (H_PI + r)) return (g + h) * INV_PI;
@@ -346,7 +346,7 @@ inline float closure_estimate_sphere(const Closure& cl, V3 inc, V3 to_light_cent
         V3 nn = dot(nor, inc) < 0.0f ? normalized(nor) : -normalized(nor);
         V3 aa = -normalized(inc);
         V3 bb = normalized(to_light_center);
-        float theta = std::acos(cos_theta_max);
+        float theta = m_acosf(cos_theta_max);
         V3 hh = normalized(aa + bb);
         float nh = rclamp(dot(nn, hh), -1.0f, 1.0f);
         float fac = ggx_d(nh, rmin(1.0f, std::sqrt(cl.roughness) + (2.0f * theta / PI_32)));

@@ -136,7 +136,7 @@ class PsyStats(C.Structure):
 class PsyRenderParams(C.Structure):
     _fields_ = [("crop_enabled", u32), ("crop_x1", u32), ("crop_y1", u32), ("crop_x2", u32), ("crop_y2", u32),
                 ("spp", u32), ("seed_override_enabled", u32), ("seed", u32), ("max_samples_per_bucket", u32),
-                ("collect_counters", u32), ("device_resident_only", u32)]
+                ("collect_counters", u32), ("device_resident_only", u32), ("strict_film_order", u32)]
 
 
 BUCKET_CB = C.CFUNCTYPE(None, C.c_void_p, u32, u32, u32, u32, C.POINTER(f32))
@@ -152,10 +152,12 @@ GEO_DTYPE = _np.dtype([("pos", "<f4", 3), ("pos_err", "<f4"), ("nor", "<f4", 3),
 
 HOST_LIB = os.path.join(HERE, "libpsy_host.so")
 CUDA_LIB = os.environ.get("PSY_CUDA_LIB", os.path.join(HERE, "libpsy_cuda.so"))  # override: kernel experiments
+CUDA_LIB_STRICT = os.path.join(HERE, "libpsy_cuda_strict.so")  # the same sources built with -DPSY_STRICT=1
+PSY_BUILD_STRICT_MATH = 1
 
 # Every symbol include/psy_cuda.h declares.
 CUDA_SYMBOLS = [
-    "psy_last_error", "psy_abi_version", "psy_init", "psy_shutdown", "psy_scene_create", "psy_scene_destroy",
+    "psy_last_error", "psy_abi_version", "psy_build_flags", "psy_init", "psy_shutdown", "psy_scene_create", "psy_scene_destroy",
     "psy_trace_rays", "psy_render_bucket", "psy_render_bucket_samples", "psy_render_image",
     "psy_render_image_shard", "psy_device_image", "psy_scene_stream", "psy_fetch_image", "psy_last_trace_timing",
 ]
@@ -186,13 +188,15 @@ def load_host():
     return lib
 
 
-def load_cuda():
+def load_cuda(path=None):
     """Loads the CUDA library.  There is no fallback: a missing library is an error."""
-    if not os.path.exists(CUDA_LIB):
-        raise RuntimeError(f"{CUDA_LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
-    lib = C.CDLL(CUDA_LIB)
+    path = path or CUDA_LIB
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(path)
     lib.psy_last_error.restype = C.c_char_p
     lib.psy_abi_version.restype = C.c_int32
+    lib.psy_build_flags.restype = C.c_uint32
     lib.psy_init.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
     lib.psy_shutdown.argtypes = [C.c_void_p]
     lib.psy_scene_create.argtypes = [C.c_void_p, C.POINTER(PsySceneDesc), C.POINTER(C.c_void_p)]
@@ -208,6 +212,6 @@ def load_cuda():
     lib.psy_fetch_image.argtypes = [C.c_void_p, C.c_void_p]
     lib.psy_last_trace_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     for name in CUDA_SYMBOLS:
-        if name not in ("psy_last_error",):
+        if name not in ("psy_last_error", "psy_build_flags"):
             getattr(lib, name).restype = C.c_int32
     return lib

@@ -17,7 +17,7 @@ import numpy as np
 from . import abi
 
 _host = None
-_cuda = None
+_cuda = {}
 
 
 def host_lib():
@@ -27,11 +27,16 @@ def host_lib():
     return _host
 
 
-def cuda_lib():
-    global _cuda
-    if _cuda is None:
-        _cuda = abi.load_cuda()
-    return _cuda
+def cuda_lib(strict=False):
+    """The CUDA library; strict=True loads libpsy_cuda_strict.so (the same kernels built with -DPSY_STRICT=1: the
+    deterministic libm replacements of include/psy_detmath.h, for bit-level parity runs against the oracle)."""
+    if strict not in _cuda:
+        lib = abi.load_cuda(abi.CUDA_LIB_STRICT if strict else abi.CUDA_LIB)
+        flags = lib.psy_build_flags()
+        if bool(flags & abi.PSY_BUILD_STRICT_MATH) != bool(strict) and "PSY_CUDA_LIB" not in __import__("os").environ:
+            raise PsyError(f"library build flags {flags:#x} do not match strict={strict}")
+        _cuda[strict] = lib
+    return _cuda[strict]
 
 
 class PsyError(RuntimeError):
@@ -122,16 +127,16 @@ class Scene:
 _ctx = {}
 
 
-def _context(device):
-    lib = cuda_lib()
-    if device not in _ctx:
+def _context(device, strict=False):
+    lib = cuda_lib(strict)
+    if (device, strict) not in _ctx:
         ctx = C.c_void_p()
         ids = (C.c_int * 1)(device)
         rc = lib.psy_init(ids, 1, C.byref(ctx))
         if rc != 0:
             raise PsyError(f"psy_init failed ({rc}): {lib.psy_last_error().decode()}")
-        _ctx[device] = ctx
-    return _ctx[device]
+        _ctx[(device, strict)] = ctx
+    return _ctx[(device, strict)]
 
 
 def stats_dict(st):
@@ -141,10 +146,11 @@ def stats_dict(st):
 class DeviceScene:
     """The scene uploaded to one GPU (PsyScene*)."""
 
-    def __init__(self, scene, device=0):
+    def __init__(self, scene, device=0, strict=False):
         self.scene = scene
-        self.lib = cuda_lib()
-        self.ctx = _context(device)
+        self.strict = bool(strict)
+        self.lib = cuda_lib(self.strict)
+        self.ctx = _context(device, self.strict)
         self.device = device
         self._s = C.c_void_p()
         rc = self.lib.psy_scene_create(self.ctx, scene.desc, C.byref(self._s))
@@ -198,8 +204,9 @@ class Renderer(Tracer):
     def output_file(self):
         return self.scene.output_file
 
-    def _params(self, max_samples_per_bucket, crop, spp, seed, counters, resident):
+    def _params(self, max_samples_per_bucket, crop, spp, seed, counters, resident, strict_film=False):
         p = abi.PsyRenderParams()
+        p.strict_film_order = 1 if strict_film else 0
         if crop is not None:
             p.crop_enabled = 1
             p.crop_x1, p.crop_y1, p.crop_x2, p.crop_y2 = [int(c) for c in crop]
@@ -213,14 +220,19 @@ class Renderer(Tracer):
         return p
 
     def render(self, max_samples_per_bucket=0, crop=None, thread_count=None, do_blender_output=False, spp=None,
-               seed=None, counters=False, on_bucket=None, device_resident_only=False):
+               seed=None, counters=False, on_bucket=None, device_resident_only=False, strict_film=False):
         """Returns (image, stats): image is float32 (res_y, res_x, 3) XYZ, row 0 = top (None when
-        device_resident_only).  thread_count is accepted for signature parity and ignored."""
-        p = self._params(max_samples_per_bucket, crop, spp, seed, counters, device_resident_only)
+        device_resident_only).  thread_count is accepted for signature parity and ignored (the GPU is the
+        worker pool).  do_blender_output=True streams every finished bucket to stdout in the reference's
+        protocol (renderer.rs:312-346) unless the caller installs its own on_bucket.
+        strict_film=True adds the samples to the film in the reference's path order (PsyRenderParams)."""
+        p = self._params(max_samples_per_bucket, crop, spp, seed, counters, device_resident_only, strict_film)
         rx, ry = self.resolution
         img = None if device_resident_only else np.zeros((ry, rx, 3), dtype=np.float32)
         st = abi.PsyStats()
         cb = None
+        if do_blender_output and on_bucket is None:
+            on_bucket = self._blender_stream(crop)
         if on_bucket is not None:
             def _cb(user, x0, y0, x1, y1, ptr):
                 n = (x1 - x0) * (y1 - y0) * 3
@@ -230,6 +242,32 @@ class Renderer(Tracer):
                                               C.byref(st), C.cast(cb, C.c_void_p) if cb else None, None),
                     "psy_render_image")
         return img, stats_dict(st)
+
+    def _blender_stream(self, crop):
+        """Default bucket sink for do_blender_output: `DIV / pct% / x0 y0 x1 y1 / base64 RGBA / BUCKET_END / DIV`."""
+        import sys
+        rx, ry = self.resolution
+        if crop is not None:
+            x1, y1, x2, y2 = [int(c) for c in crop]
+            total = (min(x2, rx - 1) - min(x1, rx - 1) + 1) * (min(y2, ry - 1) - min(y1, ry - 1) + 1)
+        else:
+            total = rx * ry
+        state = {"done": 0}
+        hl = host_lib()
+        hl.psyh_bucket_base64.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]
+        hl.psyh_bucket_base64.restype = C.c_size_t
+
+        def sink(x0, y0, x1, y1, xyz):
+            w, h = x1 - x0, y1 - y0
+            state["done"] += w * h
+            cap = ((w * h * 16 + 2) // 3) * 4 + 8
+            buf = C.create_string_buffer(cap)
+            xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+            n = hl.psyh_bucket_base64(xyz.ctypes.data, w, h, buf, cap)
+            pct = state["done"] * 100.0 / max(total, 1)
+            sys.stdout.write("DIV\n%.2f%%\n%d %d %d %d\n%s\nBUCKET_END\nDIV\n" % (pct, x0, y0, x1, y1, buf.raw[:n].decode()))
+            sys.stdout.flush()
+        return sink
 
     def render_shard(self, rank, world, max_samples_per_bucket=0, spp=None, seed=None):
         p = self._params(max_samples_per_bucket, None, spp, seed, False, True)

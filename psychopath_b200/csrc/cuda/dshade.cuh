@@ -11,6 +11,33 @@
 //   src/scene/mod.rs:28-99, src/scene/assembly.rs:46-140, src/accel/light_tree.rs:135-201
 #pragma once
 #include "dtrace.cuh"
+#include "../../../include/psy_detmath.h"
+
+// The eight libm functions of the path.  The product build calls CUDA's libdevice; the strict build
+// (-DPSY_STRICT=1, libpsy_cuda_strict.so) calls the deterministic functions the oracle's strict mode uses as well,
+// so that the CUDA path and the restated reference path agree bit for bit (DESIGN.md "Strict mode").
+#ifndef PSY_STRICT
+#define PSY_STRICT 0
+#endif
+#if PSY_STRICT
+#define PSY_SINF(x) psy_det_sinf(x)
+#define PSY_COSF(x) psy_det_cosf(x)
+#define PSY_ACOSF(x) psy_det_acosf(x)
+#define PSY_ASINF(x) psy_det_asinf(x)
+#define PSY_SIN(x) psy_det_sin(x)
+#define PSY_COS(x) psy_det_cos(x)
+#define PSY_ACOS(x) psy_det_acos(x)
+#define PSY_LOG(x) psy_det_log(x)
+#else
+#define PSY_SINF(x) sinf(x)
+#define PSY_COSF(x) cosf(x)
+#define PSY_ACOSF(x) acosf(x)
+#define PSY_ASINF(x) asinf(x)
+#define PSY_SIN(x) sin(x)
+#define PSY_COS(x) cos(x)
+#define PSY_ACOS(x) acos(x)
+#define PSY_LOG(x) log(x)
+#endif
 
 namespace psyd {
 
@@ -114,7 +141,7 @@ PSY_DEV void sobol_sample_4d(uint32_t index, uint32_t dimension_set, uint32_t se
             lane_seed ^= lane_seed >> 16;
         }
         uint32_t v = __brev(sb_lk_scramble(sob[l], lane_seed));
-        out[l] = (float)(v >> 8) * (1.0f / 16777216.0f);
+        out[l] = __uint_as_float((v >> 9) | 0x3f800000u) - 1.0f;  // sobol_burley's to_norm_floats (23-bit mantissa trick)
     }
 }
 // get_sample_4d (renderer.rs:698-725)
@@ -144,7 +171,7 @@ PSY_DEV float probit(float nf, float width) {
     const double N_LOW = 0.02425, N_HIGH = 1.0 - N_LOW;
     double x;
     if (0.0 < n && n < N_LOW) {
-        double q = sqrt(-2.0 * log(n));
+        double q = sqrt(-2.0 * PSY_LOG(n));
         x = (((((C1 * q + C2) * q + C3) * q + C4) * q + C5) * q + C6) / ((((D1 * q + D2) * q + D3) * q + D4) * q + 1.0);
     } else if (n <= N_HIGH) {
         double q = n - 0.5;
@@ -152,7 +179,7 @@ PSY_DEV float probit(float nf, float width) {
         x = (((((A1 * r + A2) * r + A3) * r + A4) * r + A5) * r + A6) * q /
             (((((B1 * r + B2) * r + B3) * r + B4) * r + B5) * r + 1.0);
     } else if (n < 1.0) {
-        double q = sqrt(-2.0 * log(1.0 - n));
+        double q = sqrt(-2.0 * PSY_LOG(1.0 - n));
         x = -(((((C1 * q + C2) * q + C3) * q + C4) * q + C5) * q + C6) / ((((D1 * q + D2) * q + D3) * q + D4) * q + 1.0);
     } else if (n == 1.0) {
         x = CUDART_INF;
@@ -189,8 +216,8 @@ PSY_NOINLINE void square_to_circle(float x, float y, float& ox, float& oy) {
         radius = -y;
         angle = QPI * (6.0f - (x / y));
     }
-    ox = radius * cosf(angle);
-    oy = radius * sinf(angle);
+    ox = radius * PSY_COSF(angle);
+    oy = radius * PSY_SINF(angle);
 }
 PSY_DEV V3 cosine_sample_hemisphere(float u, float v) {
     float a, b;
@@ -204,13 +231,13 @@ PSY_DEV V3 uniform_sample_sphere(float u, float v) {
     float z = 1.0f - (2.0f * u);
     float r = sqrtf(rmax(1.0f - (z * z), 0.0f));
     float phi = 2.0f * PSY_PI_32 * v;
-    return mk3(r * cosf(phi), r * sinf(phi), z);
+    return mk3(r * PSY_COSF(phi), r * PSY_SINF(phi), z);
 }
 PSY_NOINLINE V3 uniform_sample_cone(float u, float v, double cos_theta_max) {
     double cos_theta = (1.0 - (double)u) + ((double)u * cos_theta_max);
     double sin_theta = sqrt(1.0 - (cos_theta * cos_theta));
     double phi = (double)v * 2.0 * PSY_PI_64;
-    return mk3((float)(cos(phi) * sin_theta), (float)(sin(phi) * sin_theta), (float)cos_theta);
+    return mk3((float)(PSY_COS(phi) * sin_theta), (float)(PSY_SIN(phi) * sin_theta), (float)cos_theta);
 }
 PSY_DEV double uniform_sample_cone_pdf(double cos_theta_max) { return 1.0 / (2.0 * PSY_PI_64 * (1.0 - cos_theta_max)); }
 PSY_DEV V3 uniform_sample_triangle(V3 va, V3 vb, V3 vc, float i, float j) {
@@ -241,7 +268,7 @@ PSY_NOINLINE float spherical_triangle_solid_angle(V3 va, V3 vb, V3 vc) {
     double cos_va = rmin(rmax((s.cos_a - (s.cos_b * s.cos_c)) / (s.sin_b * s.sin_c), -1.0), 1.0);
     double cos_vb = rmin(rmax((s.cos_b - (s.cos_c * s.cos_a)) / (s.sin_c * s.sin_a), -1.0), 1.0);
     double cos_vc = rmin(rmax((s.cos_c - (s.cos_a * s.cos_b)) / (s.sin_a * s.sin_b), -1.0), 1.0);
-    double ang_va = acos(cos_va), ang_vb = acos(cos_vb), ang_vc = acos(cos_vc);
+    double ang_va = PSY_ACOS(cos_va), ang_vb = PSY_ACOS(cos_vb), ang_vc = PSY_ACOS(cos_vc);
     return (float)(ang_va + ang_vb + ang_vc - PSY_PI_64);
 }
 PSY_NOINLINE V3 uniform_sample_spherical_triangle(V3 va, V3 vb, V3 vc, float i, float j) {
@@ -251,11 +278,11 @@ PSY_NOINLINE V3 uniform_sample_spherical_triangle(V3 va, V3 vb, V3 vc, float i, 
     double cos_vb = rmin(rmax((s.cos_b - (s.cos_c * s.cos_a)) / (s.sin_c * s.sin_a), -1.0), 1.0);
     double cos_vc = rmin(rmax((s.cos_c - (s.cos_a * s.cos_b)) / (s.sin_a * s.sin_b), -1.0), 1.0);
     double sin_va = sqrt(1.0 - (cos_va * cos_va));
-    double ang_va = acos(cos_va), ang_vb = acos(cos_vb), ang_vc = acos(cos_vc);
+    double ang_va = PSY_ACOS(cos_va), ang_vb = PSY_ACOS(cos_vb), ang_vc = PSY_ACOS(cos_vc);
     double area = ang_va + ang_vb + ang_vc - PSY_PI_64;
     double area_2 = area * (double)i;
-    double ss = sin(area_2 - ang_va);
-    double t = cos(area_2 - ang_va);
+    double ss = PSY_SIN(area_2 - ang_va);
+    double t = PSY_COS(area_2 - ang_va);
     double u = t - cos_va;
     double v = ss + (sin_va * s.cos_c);
     double q_top = (((v * t) - (u * ss)) * cos_va) - v;
@@ -582,7 +609,7 @@ PSY_DEV void closure_sample(const Closure& cl, const ShadeCtx& sc, V3 inc, float
         float theta_cos = half_theta_sample(u, cl.roughness);
         float theta_sin = sqrtf(1.0f - (theta_cos * theta_cos));
         float angle = v * PSY_PI_32 * 2.0f;
-        V3 half_dir = mk3(cosf(angle) * theta_sin, sinf(angle) * theta_sin, theta_cos);
+        V3 half_dir = mk3(PSY_COSF(angle) * theta_sin, PSY_SINF(angle) * theta_sin, theta_cos);
         half_dir = normalized(zup_to_vec(half_dir, sc.nn));
         V3 out = inc - (half_dir * 2.0f * dot(inc, half_dir));
         dir = out;
@@ -602,8 +629,8 @@ PSY_DEV void closure_sample(const Closure& cl, const ShadeCtx& sc, V3 inc, float
 // only feed the two partially-occluded cases, so they are evaluated there (pure functions: same bits).
 PSY_NOINLINE float sphere_lambert(float nlcos, float rcos) {
     float rsin2 = 1.0f - (rcos * rcos);
-    float nl = acosf(nlcos);
-    float r = acosf(rcos);
+    float nl = PSY_ACOSF(nlcos);
+    float r = PSY_ACOSF(rcos);
     if (nl < (PSY_H_PI - r)) return nlcos * rsin2;
     if (!(nl < PSY_H_PI) && !(nl < (PSY_H_PI + r))) return 0.0f;
     float nlsin = sqrtf(1.0f - (nlcos * nlcos));
@@ -611,8 +638,8 @@ PSY_NOINLINE float sphere_lambert(float nlcos, float rcos) {
     float ysin = rcos / nlsin;
     float ycos2 = 1.0f - (ysin * ysin);
     float ycos = sqrtf(ycos2);
-    float g = (-2.0f * nlsin * rcos * ycos) + PSY_H_PI - asinf(ysin) + (ysin * ycos);
-    float h = nlcos * ((ycos * sqrtf(rsin2 - ycos2)) + (rsin2 * asinf(ycos / rsin)));
+    float g = (-2.0f * nlsin * rcos * ycos) + PSY_H_PI - PSY_ASINF(ysin) + (ysin * ycos);
+    float h = nlcos * ((ycos * sqrtf(rsin2 - ycos2)) + (rsin2 * PSY_ASINF(ycos / rsin)));
     if (nl < PSY_H_PI) return (nlcos * rsin2) + g - h;
     return (g + h) * PSY_INV_PI;
 }
@@ -653,7 +680,7 @@ PSY_DEV float closure_estimate_sphere(const Closure& cl, const EstimateCtx& ec, 
         V3 nn = ec.nn;
         V3 aa = ec.aa;
         V3 bb = normalized(to_light_center);
-        float theta = acosf(cos_theta_max);
+        float theta = PSY_ACOSF(cos_theta_max);
         V3 hh = normalized(aa + bb);
         float nh = rclamp(dot(nn, hh), -1.0f, 1.0f);
         float fac = ggx_d(nh, rmin(1.0f, sqrtf(cl.roughness) + (2.0f * theta / PSY_PI_32)));
@@ -924,7 +951,7 @@ __device__ __noinline__ void sample_sphere_light(const DScene& S, const PsyLight
         double cos_a = ddd <= 0.0 ? sin_theta_max : ((dd / radius) * sin_theta2) + (cos_theta * sqrt(ddd));
         double sin_a = sqrt(rmax(1.0 - (cos_a * cos_a), 0.0));
         double phi = (double)v * 2.0 * PSY_PI_64;
-        V3 s2 = mk3((float)(cos(phi) * sin_a * radius), (float)(sin(phi) * sin_a * radius), (float)(dd - (cos_a * radius)));
+        V3 s2 = mk3((float)(PSY_COS(phi) * sin_a * radius), (float)(PSY_SIN(phi) * sin_a * radius), (float)(dd - (cos_a * radius)));
         V3 sample_vec = ((x * s2.x) + (y * s2.y)) + (z * s2.z);
         normal = normalized(arr + sample_vec);
         out.pdf = (float)uniform_sample_cone_pdf(cos_theta_max);
@@ -1103,10 +1130,10 @@ __device__ __noinline__ void sample_picked_light(const DScene& S, const LightPic
                 direction = lerp3(bbv(dp + 3 * i1), bbv(dp + 3 * i1 + 3), a2);
         }
         PsyColor col = lerp_slice_color(S.light_colors + l.color_base, l.n_colors, time);
-        double solid_angle_inv = 1.0 / (2.0 * PSY_PI_64 * (1.0 - cos(radius)));
+        double solid_angle_inv = 1.0 / (2.0 * PSY_PI_64 * (1.0 - PSY_COS(radius)));
         V3 z = -normalized(direction), x2, y2;
         coordinate_system_from_vector(z, x2, y2);
-        double cos_theta_max = cos(radius);
+        double cos_theta_max = PSY_COS(radius);
         V3 sample = normalized(uniform_sample_cone(u, v, cos_theta_max));
         out.kind = 1;
         out.color = color_to_spectral(S, col, wl) * (float)solid_angle_inv;

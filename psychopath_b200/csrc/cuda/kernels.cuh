@@ -52,6 +52,8 @@ struct PathPool {
     // and 0 for a path that continues (shade kernels -> next wave's live list); see dpartition.cuh
     uint8_t* cls;
     uint8_t* alive;
+    // strict film order only: bit w is set when the path continued after wave w (k_record_alive)
+    uint8_t* whist;
 };
 
 struct Bucket {
@@ -671,6 +673,80 @@ __global__ void __launch_bounds__(32 * FILM_WARPS) k_film(PathPool P, Bucket b, 
         const uint32_t px = b.x + (q % b.w), py = b.y + (q / b.w);
         float* o = out + ((size_t)(py - oy) * stride + (px - ox)) * 3;
         o[0] = acc.x, o[1] = acc.y, o[2] = acc.z;
+    }
+}
+
+// ---- strict film order (PsyRenderParams.strict_film_order) ---------------------------------------------------
+// The reference adds a bucket's samples to the film in the order its path vector has after the wave loop's swap
+// compaction (renderer.rs:286-310): `if paths[i].next(..) { paths.swap(new_end, i); new_end += 1 }` for every wave,
+// then `for path in paths { pixel += xyz / spp }`.  Float addition does not commute with that permutation, so an image
+// that is to equal the reference's to the last bit has to replay it.  k_record_alive keeps, per slot, which waves the
+// path survived; k_film_strict replays the swaps for one bucket (<= 65536 paths, the reference's own limit: its ray
+// indices are u16, ray.rs:7) and sums every pixel's samples in the resulting order.
+__global__ void __launch_bounds__(256) k_record_alive(const uint8_t* __restrict__ alive, uint32_t n, uint32_t wave,
+                                                      uint8_t* __restrict__ whist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && alive[i] == 0) whist[i] |= (uint8_t)(1u << wave);
+}
+
+constexpr uint32_t STRICT_MAX_PATHS = 65536;
+constexpr int STRICT_THREADS = 1024;
+// order: u16[n] in shared memory (the path now at position i), hist: u8[n]; rank: u32[n] in global memory
+__global__ void __launch_bounds__(STRICT_THREADS) k_film_strict(PathPool P, Bucket b, float* out, uint32_t stride,
+                                                                uint32_t ox, uint32_t oy, float* samples_out,
+                                                                uint32_t* rank, uint32_t n_waves) {
+    extern __shared__ unsigned char strict_smem[];
+    const uint32_t n = b.w * b.h * b.spp;
+    uint16_t* order = reinterpret_cast<uint16_t*>(strict_smem);
+    uint8_t* hist = strict_smem + (size_t)n * 2;
+    const float fspp = (float)b.spp;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        order[i] = (uint16_t)i;
+        hist[i] = P.whist[i];
+        const float4 c = P.color[i];
+        if (samples_out) reinterpret_cast<float4*>(samples_out)[i] = c;
+        const V3 xyz = xyz_from_spectral(from_f4(c), P.wavelength[i]);
+        P.pending[i] = make_float4(xyz.x / fspp, xyz.y / fspp, xyz.z / fspp, 0.0f);  // (the pool column is free by now)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t pi = n;
+        for (uint32_t w = 0; w < n_waves && pi > 0; ++w) {
+            uint32_t new_end = 0;
+            for (uint32_t i = 0; i < pi; ++i) {
+                const uint16_t s = order[i];
+                if ((hist[s] >> w) & 1u) {
+                    order[i] = order[new_end];
+                    order[new_end] = s;
+                    ++new_end;
+                }
+            }
+            pi = new_end;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) rank[order[i]] = i;
+    __syncthreads();
+    // one thread per pixel: its samples in increasing rank
+    const uint32_t n_pix = b.w * b.h;
+    for (uint32_t q = threadIdx.x; q < n_pix; q += blockDim.x) {
+        V3 acc = mk3(0, 0, 0);
+        int64_t last = -1;
+        for (uint32_t k = 0; k < b.spp; ++k) {
+            uint32_t best = 0xFFFFFFFFu, best_slot = 0;
+            for (uint32_t si = 0; si < b.spp; ++si) {
+                const uint32_t r = rank[q * b.spp + si];
+                if ((int64_t)r > last && r < best) best = r, best_slot = q * b.spp + si;
+            }
+            last = (int64_t)best;
+            const float4 v = P.pending[best_slot];
+            acc = acc + mk3(v.x, v.y, v.z);
+        }
+        if (out) {
+            const uint32_t px = b.x + (q % b.w), py = b.y + (q / b.w);
+            float* o = out + ((size_t)(py - oy) * stride + (px - ox)) * 3;
+            o[0] = acc.x, o[1] = acc.y, o[2] = acc.z;
+        }
     }
 }
 

@@ -104,6 +104,7 @@ struct PsyScene {
         active_a, active_b;
     DevBuf counts, fetch, qcounts, queues, counters, image, bucket_out, samples_out;
     DevBuf pool_cls, pool_alive, part_tmp;  // per-slot byte columns and the block counts of the ordered partition
+    DevBuf pool_whist;  // strict film order: the waves each path survived (allocated on first use)
     DevBuf trace_scratch;  // k_trace_pool: child-reference stacks + saved parent spaces, [warp][level][ray]
     uint32_t pool_trace_blocks = 0;
     size_t counts_cap = 0;
@@ -242,6 +243,7 @@ PathPool make_pool(PsyScene* sc) {
     for (int k = 0; k < 6; ++k) P.ic[k] = sc->pool_ic.as<float4>() + (size_t)k * sc->pool_cap;
     P.cls = sc->pool_cls.as<uint8_t>();
     P.alive = sc->pool_alive.as<uint8_t>();
+    P.whist = sc->pool_whist.as<uint8_t>();
     return P;
 }
 
@@ -351,9 +353,20 @@ struct StageEvents {
 
 // Enqueues the whole wavefront for one bucket on the scene's stream (no host synchronisation).
 int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float* out, uint32_t stride, uint32_t ox,
-                       uint32_t oy, float* samples_out, bool counters, StageEvents* ev, uint64_t* launches) {
+                       uint32_t oy, float* samples_out, bool counters, StageEvents* ev, uint64_t* launches,
+                       bool strict_film = false) {
     cudaStream_t st = sc->ctx->stream;
     uint32_t n = b.w * b.h * b.spp;
+    if (strict_film) {
+        // the reference's own limit: RayBatch indices are u16 (ray.rs:7)
+        if (n > STRICT_MAX_PATHS)
+            return fail(PSY_ERR_LIMIT, "strict_film_order needs buckets of at most 65536 paths (pass the reference's --spb)");
+        if (sc->pool_whist.bytes < sc->pool_cap) {
+            CK(sc->pool_whist.alloc(sc->pool_cap));
+            CK(cudaFuncSetAttribute(k_film_strict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(STRICT_MAX_PATHS * 3)));
+        }
+        CK(cudaMemsetAsync(sc->pool_whist.p, 0, n, st));
+    }
     PathPool P = make_pool(sc);
     uint32_t* counts = sc->counts.as<uint32_t>() + bucket_index * COUNT_SLOTS;
     uint32_t* fetch = sc->fetch.as<uint32_t>() + bucket_index * COUNT_SLOTS;
@@ -433,6 +446,7 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
         k_shade_select<SHADE_GGX><<<shade_blocks, 128, 0, st>>>(sc->d, P, b, Q);
         k_shade_light<SHADE_GGX><<<light_blocks, PSY_LIGHT_THREADS, 0, st>>>(sc->d, P, b, Q);
         k_shade_bounce<SHADE_GGX><<<bounce_blocks, 256, 0, st>>>(sc->d, P, b, Q, next_active, next_count);
+        if (strict_film) k_record_alive<<<(n + 255) / 256, 256, 0, st>>>(P.alive, n, (uint32_t)w, P.whist);
         {
             // the next wave's live list, in slot order
             PartLists L{};
@@ -445,7 +459,11 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
         *launches += 15;
     }
     stamp(ev ? &ev->film : nullptr, true);
-    {
+    if (strict_film) {
+        // (act[0] is free by now: the rank of every path in the reference's final path order)
+        k_film_strict<<<1, STRICT_THREADS, (size_t)n * 3, st>>>(P, b, out, stride, ox, oy, samples_out, act[0], (uint32_t)WAVES);
+        *launches += WAVES;
+    } else {
         // pixels per warp: as many as still give every SM a few warps
         const uint32_t n_pix = b.w * b.h;
         uint32_t ppw = 32;
@@ -504,7 +522,7 @@ std::vector<Bucket> make_buckets(uint32_t width, uint32_t height, uint32_t start
 }
 
 int32_t render_buckets(PsyScene* sc, const std::vector<Bucket>& jobs, bool counters, PsyStats* stats, float* host_out,
-                       psy_bucket_cb cb, void* user) {
+                       psy_bucket_cb cb, void* user, bool strict_film = false) {
     cudaStream_t st = sc->ctx->stream;
     auto t0 = std::chrono::steady_clock::now();
     size_t max_n = 0;
@@ -530,7 +548,7 @@ int32_t render_buckets(PsyScene* sc, const std::vector<Bucket>& jobs, bool count
     std::vector<float> cb_buf;
     for (size_t j = 0; j < jobs.size(); ++j) {
         const Bucket& b = jobs[j];
-        rc = enqueue_bucket(sc, b, j, sc->image.as<float>(), sc->res_x, 0, 0, nullptr, counters, &ev, &launches);
+        rc = enqueue_bucket(sc, b, j, sc->image.as<float>(), sc->res_x, 0, 0, nullptr, counters, &ev, &launches, strict_film);
         if (rc) return rc;
         if (cb) {
             // Blender-style streaming: hand the finished bucket to the caller (renderer.rs:312-346)
@@ -581,6 +599,7 @@ extern "C" {
 
 const char* psy_last_error(void) { return g_err.c_str(); }
 int32_t psy_abi_version(void) { return PSY_ABI_VERSION; }
+uint32_t psy_build_flags(void) { return (PSY_STRICT ? PSY_BUILD_STRICT_MATH : 0u); }
 
 int32_t psy_init(const int* device_ids, int n_devices, PsyContext** out) {
     if (!out) return fail(PSY_ERR_INVALID, "psy_init: out is null");
@@ -1116,6 +1135,8 @@ static int32_t image_jobs(PsyScene* sc, const PsyRenderParams* p, std::vector<Bu
     }
     size_t spb = (p && p->max_samples_per_bucket) ? p->max_samples_per_bucket
                                                   : default_pool((uint64_t)width * height * spp, world);
+    // the film order of the reference depends on its bucket list: strict renders use the reference's default --spb
+    if (p && p->strict_film_order && !p->max_samples_per_bucket) spb = 4096;
     // a caller that wants every finished bucket (Blender's progressive display) gets buckets of a viewable size
     if (streaming && !(p && p->max_samples_per_bucket)) spb = std::min<size_t>(spb, 4u << 20);
     jobs = make_buckets(width, height, sx, sy, spp, seed, spb);
@@ -1133,7 +1154,8 @@ int32_t psy_render_image(PsyScene* sc, const PsyRenderParams* p, float* xyz_out,
     int32_t rc = image_jobs(sc, p, jobs, 1, cb != nullptr);
     if (rc) return rc;
     if (sc->image.p) CK(cudaMemsetAsync(sc->image.p, 0, sc->image.bytes, sc->ctx->stream));
-    return render_buckets(sc, jobs, p && p->collect_counters, stats, resident ? nullptr : xyz_out, cb, user);
+    return render_buckets(sc, jobs, p && p->collect_counters, stats, resident ? nullptr : xyz_out, cb, user,
+                          p && p->strict_film_order);
 }
 
 int32_t psy_render_image_shard(PsyScene* sc, const PsyRenderParams* p, uint32_t rank, uint32_t world, PsyStats* stats) {

@@ -79,8 +79,29 @@ def load():
     lib.oracle_xyz_from_spectral.argtypes = [F, f32, F]
     lib.oracle_xyz_from_spectral.restype = None
     lib.oracle_tri_intersect.argtypes = [F, F, f32, F, F]
+    lib.oracle_set_strict_math.argtypes = [C.c_int]
+    lib.oracle_set_strict_math.restype = None
+    lib.oracle_set_debug.argtypes = [u32, u32, u32]
+    lib.oracle_set_debug.restype = None
+    lib.oracle_det_f64.argtypes = [C.c_int, C.c_double]
+    lib.oracle_det_f64.restype = C.c_double
+    lib.oracle_det_f32.argtypes = [C.c_int, f32]
+    lib.oracle_det_f32.restype = f32
     _lib = lib
     return lib
+
+
+class strict_math:
+    """Context manager: the oracle calls include/psy_detmath.h instead of glibc for sin/cos/acos/asin/log, like
+    the strict build of the CUDA library (libpsy_cuda_strict.so)."""
+
+    def __enter__(self):
+        load().oracle_set_strict_math(1)
+        return self
+
+    def __exit__(self, *exc):
+        load().oracle_set_strict_math(0)
+        return False
 
 
 def trace_rays(desc, rays, want_geo=False):

@@ -26,7 +26,7 @@ def test_cuda_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib.psy_abi_version.restype = C.c_int32
-    assert lib.psy_abi_version() == 1
+    assert lib.psy_abi_version() == 2
 
 
 def test_struct_layout_matches_c():
