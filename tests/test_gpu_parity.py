@@ -104,8 +104,11 @@ def test_probe_rays_bit_exact(name):
 
 @pytest.mark.parametrize("name", SCENES)
 def test_per_sample_radiance(name):
-    """LightPath.color of every sample (same seed, same Sobol/hash sequences) against the oracle.
-    libm vs libdevice ulp differences in sin/cos/log/acos perturb a few paths; the bulk must agree."""
+    """LightPath.color of every sample (same seed, same Sobol/hash sequences) against the oracle, product build.
+    libdevice vs glibc ulp differences in sin/cos/log/acos perturb a few paths (with the same libm on both sides
+    every sample is bit-identical: tests/test_gpu_strict.py).  Measured on B200 (profiles/r2_parity.json): at most
+    2.6e-4 of the samples beyond 1e-3, image rel-L2 between 5e-9 and 3.4e-4 at 4-8 spp; the gates are SURVEY.md
+    8(c)'s rel-L2 <= 2e-3 and 1e-3 of the samples."""
     scene = make_scene(name)
     d = scene.desc.contents
     r = api.Renderer(scene)
@@ -114,15 +117,18 @@ def test_per_sample_radiance(name):
     gs, st = r.render_bucket_samples(x0, y0, w, h, 4, d.seed)
     oxyz, osamp, ost = O.render_bucket(scene.desc, x0, y0, w, h, 4, d.seed, want_samples=True)
     assert st["ray_count"] > 0
-    # identical path counts per wave is too strict (a perturbed path may die earlier); total within 0.5 %
-    assert abs(int(st["ray_count"]) - int(ost.ray_count)) <= 0.005 * ost.ray_count + 4
+    # identical path counts per wave is too strict (a perturbed path may die earlier); total within 0.1 %
+    assert abs(int(st["ray_count"]) - int(ost.ray_count)) <= 0.001 * ost.ray_count + 4
+    # no non-finite sample on either side in these scenes (where the reference's arithmetic does produce one, the
+    # strict build reproduces it at the same sample: test_gpu_strict.py::test_config_c5_non_finite_samples...)
+    assert np.isfinite(gs).all() and np.isfinite(osamp).all()
     err = np.abs(gs - osamp).max(axis=-1) / (np.abs(osamp).max(axis=-1) + 1e-3)
-    assert (err > 1e-3).mean() < 0.02, f"{(err > 1e-3).mean():.4f} of samples beyond 1e-3"
-    assert np.isfinite(gs).all() == np.isfinite(osamp).all()
+    assert (err > 1e-3).mean() <= 1e-3, f"{(err > 1e-3).mean():.5f} of samples beyond 1e-3"
     gxyz, _ = r.render_bucket(x0, y0, w, h, 4, d.seed)
-    fin = np.isfinite(oxyz).all(axis=-1) & np.isfinite(gxyz).all(axis=-1)
-    rel_l2 = np.linalg.norm((gxyz - oxyz)[fin]) / max(np.linalg.norm(oxyz[fin]), 1e-20)
-    assert rel_l2 < 2e-2, rel_l2
+    rel_l2 = np.linalg.norm(gxyz - oxyz) / max(np.linalg.norm(oxyz), 1e-20)
+    rmse = float(np.sqrt(((gxyz - oxyz).astype(np.float64) ** 2).mean()))
+    print(f"[parity] {name}: rel-L2 {rel_l2:.3e} rmse {rmse:.3e} samples beyond 1e-3 {(err > 1e-3).mean():.2e}")
+    assert rel_l2 <= 2e-3, rel_l2
 
 
 def test_image_tiling_and_determinism():
@@ -143,17 +149,37 @@ def test_image_tiling_and_determinism():
     assert crop[:5].sum() == 0 and crop[21:].sum() == 0
 
 
-def test_image_vs_oracle_cornell():
-    """BASELINE config C1 shape (Cornell box) at reduced size: image relative-L2 against the oracle."""
+def test_image_vs_oracle_cornell_full_size():
+    """BASELINE config 0 at its size (cornell_box.psy, 512 x 512, 16 spp, seed 1), product build: image
+    relative-L2 against the oracle.  Measured 5.1e-6 (RMSE 1.3e-5) on B200, profiles/r2_parity.json."""
     s = api.Scene.from_psy_string(cornell_text())
-    s.set_render(res=(96, 96), spp=16, seed=1)
+    s.set_render(res=(512, 512), spp=16, seed=1)
     r = api.Renderer(s)
     img, st = r.render()
     ref, ost, _ = O.render_image(s.desc, 16, 1, spb=4096, threads=0)
     rel_l2 = np.linalg.norm(img - ref) / np.linalg.norm(ref)
-    rmse = float(np.sqrt(((img - ref) ** 2).mean()))
-    assert rel_l2 < 1e-2, (rel_l2, rmse)
-    assert abs(int(st["ray_count"]) - int(ost.ray_count)) <= 0.005 * ost.ray_count
+    rmse = float(np.sqrt(((img - ref).astype(np.float64) ** 2).mean()))
+    print(f"[parity] C1 full size: rel-L2 {rel_l2:.3e} rmse {rmse:.3e}")
+    assert rel_l2 <= 5e-5 and rmse <= 1e-4, (rel_l2, rmse)
+    assert abs(int(st["ray_count"]) - int(ost.ray_count)) <= 1e-4 * ost.ray_count
+
+
+def test_image_vs_oracle_c2_and_c5_crops():
+    """BASELINE config 1 (cube.psy 1080p, 64 spp, DoF + camera motion) and the headline C5 scene (4K), product
+    build, on crops the oracle renders in seconds.  Measured rel-L2 2.3e-5 / 5.7e-5 (profiles/r2_parity.json)."""
+    import bench
+    s = api.Scene.from_psy_string(cube_text(res=(1920, 1080), spp=64, camera_motion=True))
+    kw = dict(bench.WORKLOADS["C5"])
+    for name, scene, seed, crop in [("C2", s, s.seed, (704, 348, 704 + 511, 348 + 383)),
+                                    ("C5", api.Scene.synth_instanced(**kw), kw["seed"], (1792, 1008, 1792 + 255, 1008 + 143))]:
+        r = api.Renderer(scene)
+        img, st = r.render(spp=64, seed=seed, crop=crop)
+        ref, ost, _ = O.render_image(scene.desc, 64, seed, spb=4096, crop=crop)
+        assert np.isfinite(img).all() and np.isfinite(ref).all()
+        rel_l2 = np.linalg.norm(img - ref) / np.linalg.norm(ref)
+        print(f"[parity] {name} crop: rel-L2 {rel_l2:.3e}")
+        assert rel_l2 <= 5e-4, (name, rel_l2)
+        assert abs(int(st["ray_count"]) - int(ost.ray_count)) <= 1e-4 * ost.ray_count + 4
 
 
 def test_counters_match_oracle():
