@@ -228,6 +228,17 @@ def test_cli_drop_in(tmp_path):
     assert "Rays traced:" in out.stdout and "Writing image to disk into 'test_renders/cube.png'" in out.stdout
     img = cv2.imread(str(tmp_path / "test_renders" / "cube.png"))
     assert img is not None and img.shape[:2] == (540, 960) and img.mean() > 5
+    # the file is the sRGB-quantised render, upright (image row 0 = top row of the PNG, ADVICE r1 / image.rs:138-165)
+    sc = api.Scene.from_psy_file(scene)
+    xyz, _ = api.Renderer(sc).render(spp=4)
+    m = np.array([[2.6896551724, -1.2758620690, -0.4137931034], [-1.0221081721, 1.9782866167, 0.0438215555],
+                  [0.0612244898, -0.2244897959, 1.1632653061]], dtype=np.float32)  # xyz_to_rec709_e
+    rgb = np.clip(xyz @ m.T, 0, None)
+    srgb = np.where(rgb < 0.0031308, rgb * 12.92, 1.055 * np.power(np.maximum(rgb, 1e-12), 1 / 2.4) - 0.055)
+    want = (np.clip(srgb, 0, 1) * 255).astype(np.int32)
+    got = img[..., ::-1].astype(np.int32)
+    assert np.abs(got - want).mean() < 0.5, np.abs(got - want).mean()
+    assert np.abs(got[::-1] - want).mean() > 2.0  # ... and not its mirror image
     # stdin + serialized output, as PsychoBlend drives it (psychoblend/render.py:37-63,191-230)
     text = open(scene).read() + "\n__PSY_EOF__\n"
     out = subprocess.run([exe, "--spb", "65536", "--serialized_output", "--use_stdin", "--spp", "1"], cwd=tmp_path,

@@ -41,7 +41,9 @@ def test_png_roundtrip(tmp_path):
     assert got.shape == (img.shape[0], img.shape[1], 4) and (got[..., 3] == 255).all()
     rgb = np.clip(img @ M.T, 0, None)
     srgb = np.where(rgb < 0.0031308, rgb * 12.92, 1.055 * np.power(np.maximum(rgb, 1e-12), 1 / 2.4) - 0.055)
-    want = (np.clip(srgb, 0, 1) * 255).astype(np.uint8)[::-1]  # rows bottom-up (image.rs:147)
+    # upright: image row 0 (the reddish top row) is the first row of the file.  image.rs:147 reverses the rows only
+    # because png_encode_mini takes them bottom-to-top and reverses them again.
+    want = (np.clip(srgb, 0, 1) * 255).astype(np.uint8)
     assert np.abs(got[..., 2::-1][..., :3].astype(int) - want.astype(int)).max() <= 1
 
 
