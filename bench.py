@@ -33,8 +33,13 @@ sys.path.insert(0, os.path.join(REPO, "tests"))
 
 WORKLOADS = {
     # name: (scene kwargs, resolution, spp, seed)
+    # motion_pct=1250: the cluster instances move far enough over the shutter (drift up to 5 units, rotation up to 0.6
+    # rad) that the root assembly's BVH keeps 2-key bounds on its lower nodes; round 1 ran the
+    # same scene with motion_pct=100, which the builder's 1.4x union rule collapses to single-key nodes ("C5r1")
     "C5": dict(asset_quads=500, n_assets=4, n_clusters=100, inst_per_cluster=10, lights_per_cluster=10,
-               cluster_xform_keys=2, res=(3840, 2160), spp=256, seed=5),
+               cluster_xform_keys=2, res=(3840, 2160), spp=256, seed=5, motion_pct=1250),
+    "C5r1": dict(asset_quads=500, n_assets=4, n_clusters=100, inst_per_cluster=10, lights_per_cluster=10,
+                 cluster_xform_keys=2, res=(3840, 2160), spp=256, seed=5, motion_pct=100),
     "C4": dict(asset_quads=500, n_assets=4, n_clusters=100, inst_per_cluster=10, lights_per_cluster=10,
                cluster_xform_keys=1, res=(1920, 1080), spp=64, seed=4),
     "tiny": dict(asset_quads=40, n_assets=4, n_clusters=16, inst_per_cluster=6, lights_per_cluster=4,
@@ -42,7 +47,8 @@ WORKLOADS = {
 }
 WORKLOAD_DESC = {
     "C5": "C5: synthetic hierarchical-instancing scene (100 clusters x (10 instances of 4 x 500k-tri assets + 10 area "
-          "lights), 2 transform keys per cluster instance), 3840x2160, 256 spp",
+          "lights), 2 transform keys per cluster instance, motion-blurred cluster nodes), 3840x2160, 256 spp",
+    "C5r1": "C5 as round 1 ran it (cluster motion small enough to collapse to single-key BVH nodes), 3840x2160, 256 spp",
     "C4": "C4: synthetic hierarchical-instancing scene, 1920x1080, 64 spp",
     "tiny": "tiny instanced scene (harness self-test), 320x180, 8 spp",
 }
@@ -146,6 +152,36 @@ def cpu_sample(scene, spp, seed, target_s=15.0, threads=0):
             "buckets": done, "rays": int(st.ray_count), "samples": int(st.samples), "threads": int(st.threads)}
 
 
+def c3_leg(api, device):
+    """BASELINE config 2 on one GPU: 10.0 M-triangle displaced mesh, 4 deformation + 4 transform keys, 1920x1080,
+    128 spp.  Two timed frames after one warm-up, scene resident; visit counts from the counters build at 8 spp."""
+    t0 = time.time()
+    s = api.Scene.synth_displaced_grid(2240, n_vert_keys=4, n_xform_keys=4, res=(1920, 1080), spp=128, seed=3)
+    build_s = time.time() - t0
+    t0 = time.time()
+    r = api.Renderer(s, device=device)
+    upload_s = time.time() - t0
+    r.render(device_resident_only=True)
+    t0 = time.perf_counter()
+    rays = 0
+    trace_s = 0.0
+    for _ in range(2):
+        st = r.render(device_resident_only=True)[1]
+        rays += int(st["ray_count"])
+        trace_s += st["trace_time"]
+    dt = time.perf_counter() - t0
+    _, cst = r.render(spp=8, counters=True, device_resident_only=True)
+    b_ray, per_ray = algorithmic_bytes_per_ray(cst, keys_vert=2, keys_xform=2)
+    pk, _ = peaks()
+    out = {"workload": "C3: 10.0 M-triangle displaced mesh, 4 deformation + 4 transform keys, 1920x1080, 128 spp",
+           "value": rays / dt / 1e6, "unit": "Mrays/s", "ms_per_frame": dt / 2 * 1e3, "trace_ms_per_frame": trace_s / 2 * 1e3,
+           "msamples_s": 2 * 1920 * 1080 * 128 / dt / 1e6, "per_ray": per_ray, "bytes_per_ray": b_ray,
+           "roofline_frac_trace": (rays * b_ray) / max(trace_s, 1e-12) / 1e9 / pk["hbm_gbs"],
+           "host_build_s": build_s, "upload_s": upload_s, "triangles": int(s.desc.contents.n_tris)}
+    r.close()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -187,6 +223,9 @@ def main():
                     help="path-pool size (paths in flight per GPU); 0 = the library's default: the whole image up to "
                          "64 Mi paths, at least ~6 buckets per GPU when tiled across GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c3", action="store_true",
+                    help="skip the extra leg on BASELINE config 2 (10 M-triangle mesh, 4+4 motion keys: every BVH node a "
+                         "motion node)")
     ap.add_argument("--counter-spp", type=int, default=8)
     ap.add_argument("--spp", type=int, default=0, help="override spp (profiling runs only; not the headline config)")
     args = ap.parse_args()
@@ -363,12 +402,17 @@ def main():
                     "trace_share_of_step": float(t[3]) * 1e-3 / dev_s,
                     "roofline_mrays_s": pk["hbm_gbs"] * 1e9 / b_ray / 1e6,
                     "note": "visit counts measured by the counters build at %d spp" % min(args.counter_spp, spp)}
-        if world == 1 and not args.no_cpu_baseline:
+        if not args.no_cpu_baseline:
             c = cpu_sample(scene, spp, seed, target_s=15.0)
             cpu = {"value": c["mrays_s"], "unit": "Mrays/s", "cores": c["threads"], "kind": "port",
                    "msamples_s": c["msamples_s"], "seconds": c["seconds"],
                    "sample": f"{c['buckets']} Hilbert-ordered 4x4-pixel buckets x {spp} spp of the same scene "
                              f"({c['samples']} samples, {c['rays']} rays)"}
+
+    # ---- extra leg (rank 0, one GPU): BASELINE config 2, where EVERY node visit lerps two time keys ----
+    c3 = None
+    if rank == 0 and name == "C5" and not args.no_c3 and not args.spp:
+        c3 = c3_leg(api, local_rank)
 
     if rank == 0:
         line = {"metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": world,
@@ -379,7 +423,9 @@ def main():
                            "l2": "working set (path pool %d MB + scene) exceeds the 126 MB L2" % (pool_paths * 390 >> 20)},
                 "msamples_s": msamples, "rays_per_step": rays / args.steps, "samples_per_step": samples_per_step,
                 "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
-                "stage_ms_per_step_rank0": stage, "host_build_s": build_s, "upload_s": upload_s}
+                "stage_ms_per_step_rank0": stage, "host_build_s": build_s, "upload_s": upload_s,
+                "motion_nodes_per_ray": roofline["per_ray"]["motion_nodes_per_ray"] if roofline else None,
+                "c3": c3}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

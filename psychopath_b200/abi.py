@@ -170,7 +170,7 @@ def load_host():
     lib.psyh_load_psy_file.argtypes = [C.c_char_p, u32, C.POINTER(C.c_void_p)]
     lib.psyh_count_scenes.argtypes = [C.c_char_p, C.POINTER(u32)]
     lib.psyh_synth_displaced_grid.argtypes = [u32] * 7 + [C.POINTER(C.c_void_p)]
-    lib.psyh_synth_instanced.argtypes = [u32] * 10 + [C.POINTER(C.c_void_p)]
+    lib.psyh_synth_instanced.argtypes = [u32] * 11 + [C.POINTER(C.c_void_p)]
     lib.psyh_scene_desc.argtypes = [C.c_void_p]
     lib.psyh_scene_desc.restype = C.POINTER(PsySceneDesc)
     lib.psyh_build_seconds.argtypes = [C.c_void_p]

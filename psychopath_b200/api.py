@@ -84,11 +84,13 @@ class Scene:
 
     @classmethod
     def synth_instanced(cls, asset_quads=500, n_assets=4, n_clusters=100, inst_per_cluster=10, lights_per_cluster=10,
-                        cluster_xform_keys=2, res=(1920, 1080), spp=64, seed=4):
+                        cluster_xform_keys=2, res=(1920, 1080), spp=64, seed=4, motion_pct=100):
+        """motion_pct scales the cluster instances' motion over the shutter (100: drift <= 0.4 units, which the
+        builder's 1.4x union rule merges into single-key bounds; 1250: BASELINE config 4's motion-blurred scene)."""
         h = C.c_void_p()
         cls._check(host_lib().psyh_synth_instanced(asset_quads, n_assets, n_clusters, inst_per_cluster,
                                                    lights_per_cluster, cluster_xform_keys, res[0], res[1], spp, seed,
-                                                   C.byref(h)))
+                                                   motion_pct, C.byref(h)))
         return cls(h)
 
     def set_render(self, res=None, spp=0, seed=None):

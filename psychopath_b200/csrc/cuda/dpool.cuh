@@ -285,20 +285,28 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 rcb[2 * R + r] = __float_as_uint(op.z);
                 rcb[3 * R + r] = __float_as_uint(pre.sx), rcb[4 * R + r] = __float_as_uint(pre.sy);
                 rcb[5 * R + r] = __float_as_uint(pre.sz);
-                top = S.root_bvh;
+                top = S.root_bvh2;
             }
         } else if (k == Q_NODE) {
             // ---- one internal node (bvh4.rs:118-166, bbox4.rs:63-97)
             if (act) {
+                // blob reference (dscene.cuh): unit offset of the node, and how many time keys follow its header
                 const uint32_t ref = ST(PF_TOP, r);
-                const uint4* np = S.nodes + (size_t)ref * 8u;
-                // the whole 128-byte node at once (the static bounds are unused, but valid memory, for motion nodes)
-                uint4 child, meta;  // meta: traversal_code, n_keys, key_base, n_children
+                const uint32_t unit = ref & NODE2_OFF_MASK, kc = ref >> NODE2_KC_SHIFT;
+                const uint4* np = S.nodes2 + unit;
+                // header and first key at once (for motion nodes the first key is replaced below; its memory is valid)
+                uint4 child, meta;  // meta: traversal_code, n_keys, -, n_children
                 float4 bx0, bx1, by0, by1, bz0, bz1;
-                if (S.nodes_tex) {
+                // motion nodes: which keys the ray's time falls between is known from the reference alone, so the keys
+                // are requested together with the header — one round trip
+                uint32_t mk_i1 = 0;
+                float mk_a2 = 0.0f;
+                bool mk_blend = false;
+                if (kc != 0u && kc != 7u) mk_blend = lerp_slice_keys(kc + 1u, STF(PF_TIME, r), mk_i1, mk_a2);
+                if (S.nodes_tex && kc == 0u) {
                     // node fetches go through the texture pipe, next to the LSU pipe that carries everything else
                     // (a scene too large for a linear texture has no texture object and takes the other branch)
-                    const int tn = (int)(ref * 8u);
+                    const int tn = (int)unit;
                     child = tex1Dfetch<uint4>(S.nodes_tex, tn);
                     meta = tex1Dfetch<uint4>(S.nodes_tex, tn + 1);
 #define PSY_TEXF4(i)                                                                                          \
@@ -312,9 +320,23 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 } else {
                     child = __ldg(np);
                     meta = __ldg(np + 1);
-                    const float4* bp = reinterpret_cast<const float4*>(np + 2);
+                    const float4* bp = reinterpret_cast<const float4*>(np + 2) + 6u * mk_i1;
                     bx0 = __ldg(bp), bx1 = __ldg(bp + 1), by0 = __ldg(bp + 2), by1 = __ldg(bp + 3), bz0 = __ldg(bp + 4),
                     bz1 = __ldg(bp + 5);
+                    if (mk_blend) {
+                        const float ia = 1.0f - mk_a2, a2 = mk_a2;
+#define PSY_LERP4(A, B) \
+    A = make_float4((A.x * ia) + (B.x * a2), (A.y * ia) + (B.y * a2), (A.z * ia) + (B.z * a2), (A.w * ia) + (B.w * a2))
+                        const float4 c0 = __ldg(bp + 6), c1 = __ldg(bp + 7), c2 = __ldg(bp + 8), c3 = __ldg(bp + 9),
+                                     c4 = __ldg(bp + 10), c5 = __ldg(bp + 11);
+                        PSY_LERP4(bx0, c0);
+                        PSY_LERP4(bx1, c1);
+                        PSY_LERP4(by0, c2);
+                        PSY_LERP4(by1, c3);
+                        PSY_LERP4(bz0, c4);
+                        PSY_LERP4(bz1, c5);
+#undef PSY_LERP4
+                    }
                 }
                 flags = ST(PF_FLAGS, r);
                 PSY_LOAD_SP()
@@ -324,22 +346,20 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 const V3 di = mk3(STF(fo + 3, r), STF(fo + 4, r), STF(fo + 5, r));
                 const uint32_t space = in_mesh ? (flags >> RF_MSPACE_SHIFT) & 15u : (flags >> 1) & 15u;  // finite | octant << 1
                 const float max_t = STF(PF_MAXT, r);
-                if (meta.y != 1u) {
-                    if (COUNT) cnt.motion_node_visits += 1;
+                if (kc == 7u) {
+                    // 8 or more time keys: the count comes from the header (a dependent fetch, like the ABI layout)
                     uint32_t i1;
                     float a2;
                     const bool blend = lerp_slice_keys(meta.y, STF(PF_TIME, r), i1, a2);
-                    const int tk = (int)((meta.z + i1) * 6u);
-                    const float4* k0 = S.motion_bounds + (size_t)(meta.z + i1) * 6u;
-                    const bool mtex = S.motion_tex != 0ull;
-#define PSY_MB(i) (mtex ? tex1Dfetch<float4>(S.motion_tex, tk + (i)) : __ldg(k0 + (i)))
-                    bx0 = PSY_MB(0), bx1 = PSY_MB(1), by0 = PSY_MB(2), by1 = PSY_MB(3), bz0 = PSY_MB(4), bz1 = PSY_MB(5);
+                    const float4* k0 = reinterpret_cast<const float4*>(np + 2) + 6u * i1;
+                    bx0 = __ldg(k0), bx1 = __ldg(k0 + 1), by0 = __ldg(k0 + 2), by1 = __ldg(k0 + 3), bz0 = __ldg(k0 + 4),
+                    bz1 = __ldg(k0 + 5);
                     if (blend) {
                         const float ia = 1.0f - a2;
 #define PSY_LERP4(A, B) \
     A = make_float4((A.x * ia) + (B.x * a2), (A.y * ia) + (B.y * a2), (A.z * ia) + (B.z * a2), (A.w * ia) + (B.w * a2))
-                        const float4 c0 = PSY_MB(6), c1 = PSY_MB(7), c2 = PSY_MB(8), c3 = PSY_MB(9), c4 = PSY_MB(10),
-                                     c5 = PSY_MB(11);
+                        const float4 c0 = __ldg(k0 + 6), c1 = __ldg(k0 + 7), c2 = __ldg(k0 + 8), c3 = __ldg(k0 + 9),
+                                     c4 = __ldg(k0 + 10), c5 = __ldg(k0 + 11);
                         PSY_LERP4(bx0, c0);
                         PSY_LERP4(bx1, c1);
                         PSY_LERP4(by0, c2);
@@ -348,8 +368,8 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                         PSY_LERP4(bz1, c5);
 #undef PSY_LERP4
                     }
-#undef PSY_MB
                 }
+                if (COUNT && kc != 0u) cnt.motion_node_visits += 1;
                 if (COUNT) cnt.node_visits += 1;
                 const float ADJ = 1.00000024f;
                 uint32_t hits = 0;
@@ -575,7 +595,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                     } else {
                         PSY_PUSH(MARK_POP_ASM)
                     }
-                    top = r1.x;
+                    top = r0.w;  // BVH root as a blob reference (r1.x is the ABI reference k_trace uses)
                 } else if (light) {
                     const V3 ol = own ? xf_point(xform, orig) : mk3(STF(PF_OL + 0, r), STF(PF_OL + 1, r), STF(PF_OL + 2, r));
                     const float max_t = STF(PF_MAXT, r);

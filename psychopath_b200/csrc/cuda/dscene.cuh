@@ -35,17 +35,25 @@ struct DMesh {
 #ifndef PSY_POOL_NODE_TEX
 #define PSY_POOL_NODE_TEX 1
 #endif
-// The motion-key bounds stay on the LSU pipe: 12 more texture fetches per motion node made BASELINE config 2
-// (every node a motion node) 3 % slower (trace 1271 vs 1230 ms per frame).
-#ifndef PSY_POOL_MOTION_TEX
-#define PSY_POOL_MOTION_TEX 0
-#endif
+
+// k_trace_pool's node store ("blob"): variable-size records addressed in 16-byte units, the time keys of a node
+// directly behind its header, so that a motion node costs ONE memory round trip instead of header -> keys:
+//   unit 0      child references (inner children re-encoded, see below; leaves as in the ABI)
+//   unit 1      traversal_code, n_keys, 0, n_children
+//   unit 2+6k.. bounds of time key k: xmin[4] xmax[4] ymin[4] ymax[4] zmin[4] zmax[4]
+// An inner child reference carries what the fetch needs before the node is seen:
+//   bit 31 = 0 | bits 28-30: min(n_keys, 8) - 1 | bits 0-27: unit offset of the node
+// (key count code 7 = "8 or more keys": the count is then read from the header, a dependent fetch).
+// A static node is 8 units = 128 bytes, exactly the ABI's PsyBvh4Node.
+constexpr uint32_t NODE2_OFF_MASK = 0x0FFFFFFFu;
+constexpr uint32_t NODE2_KC_SHIFT = 28;
 
 struct DScene {
     // acceleration structures
-    const uint4* nodes;          // PsyBvh4Node as 8 x 16 B
-    unsigned long long nodes_tex; // the same buffer as a linear uint4 texture object (PSY_POOL_NODE_TEX)
-    unsigned long long motion_tex; // motion_bounds as a linear float4 texture object (PSY_POOL_MOTION_TEX)
+    const uint4* nodes;          // PsyBvh4Node as 8 x 16 B (k_trace, the one-ray-per-lane kernel)
+    const uint4* nodes2;         // the blob described above (k_trace_pool)
+    uint32_t root_bvh2;          // root assembly's BVH root as a blob reference
+    unsigned long long nodes_tex; // the blob as a linear uint4 texture object (PSY_POOL_NODE_TEX)
     const float4* motion_bounds; // PsyBBox4 as 6 x float4 per key
     // geometry: per triangle (leaf order) 3*k float4: [v0 keys][v1 keys][v2 keys]; v0-key0 .w = original index
     const float4* tri_verts;

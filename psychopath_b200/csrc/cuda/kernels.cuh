@@ -259,6 +259,32 @@ __global__ void __launch_bounds__(256) k_gather_tri_verts(const uint4* __restric
     out[(size_t)tv_base + i] = make_float4(v[0], v[1], v[2], w);
 }
 
+// Scene upload: the node blob of k_trace_pool (dscene.cuh) from the ABI's node and motion-key arrays.
+// unit_off[i] = first 16-byte unit of node i.  One thread per node.
+PSY_DEV uint32_t node2_ref(uint32_t c, const uint4* __restrict__ nodes, const uint32_t* __restrict__ unit_off) {
+    if (c & PSY_CHILD_LEAF_BIT) return c;  // leaves and PSY_NONE
+    const uint32_t nk = nodes[(size_t)c * 8u + 1u].y;
+    return ((min(nk, 8u) - 1u) << NODE2_KC_SHIFT) | unit_off[c];
+}
+__global__ void __launch_bounds__(256) k_build_node_blob(const uint4* __restrict__ nodes, const float4* __restrict__ motion,
+                                                         const uint32_t* __restrict__ unit_off, uint32_t n_nodes,
+                                                         uint4* __restrict__ blob) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const uint4* src = nodes + (size_t)i * 8u;
+    const uint4 child = src[0], meta = src[1];
+    uint4* dst = blob + unit_off[i];
+    dst[0] = make_uint4(node2_ref(child.x, nodes, unit_off), node2_ref(child.y, nodes, unit_off),
+                        node2_ref(child.z, nodes, unit_off), node2_ref(child.w, nodes, unit_off));
+    dst[1] = make_uint4(meta.x, meta.y, 0u, meta.w);
+    if (meta.y == 1u) {
+        for (int k = 0; k < 6; ++k) dst[2 + k] = src[2 + k];
+    } else {
+        const uint4* keys = reinterpret_cast<const uint4*>(motion) + (size_t)meta.z * 6u;
+        for (uint32_t k = 0; k < meta.y * 6u; ++k) dst[2 + k] = keys[k];
+    }
+}
+
 // Probe rays through the production trace kernel: load them into the path pool ...
 __global__ void __launch_bounds__(256) k_probe_load(const PsyRay* __restrict__ rays, uint32_t n, PathPool P, uint32_t* active,
                                                     uint32_t* count0) {

@@ -94,7 +94,7 @@ struct PsyScene {
     DScene d{};
     uint32_t res_x = 0, res_y = 0, spp = 0, seed = 0;
     uint64_t upload_bytes = 0;
-    DevBuf nodes, motion, tri_verts, tris, normals, meshes, lights, light_shape, light_colors, objects, shaders,
+    DevBuf nodes, node_blob, motion, tri_verts, tris, normals, meshes, lights, light_shape, light_colors, objects, shaders,
         assemblies, instances, light_instances, light_inst_local, xforms, light_nodes, lt_bounds, paths, path_xforms,
         path_inv, path_recs, path_static, cam_xforms, cam_tfovs, cam_aperture, cam_focus, distant, world_floats, meng;
     // path pool
@@ -115,7 +115,6 @@ struct PsyScene {
     std::mutex mu;
     ~PsyScene() {
         if (d.nodes_tex) cudaDestroyTextureObject((cudaTextureObject_t)d.nodes_tex);
-        if (d.motion_tex) cudaDestroyTextureObject((cudaTextureObject_t)d.motion_tex);
         for (auto e : events) cudaEventDestroy(e);
     }
 };
@@ -774,6 +773,18 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
             o += (size_t)pm.tri_count * 3 * pm.n_keys;
         }
     }
+    // k_trace_pool's node blob (dscene.cuh): where every node starts, in 16-byte units, and the re-encoded references
+    std::vector<uint32_t> unit_off(s->n_nodes);
+    uint64_t blob_units = 0;
+    for (uint32_t i = 0; i < s->n_nodes; ++i) {
+        unit_off[i] = (uint32_t)blob_units;
+        blob_units += 2u + 6u * (uint64_t)s->nodes[i].n_keys;
+        if (blob_units > (uint64_t)NODE2_OFF_MASK) return fail(PSY_ERR_LIMIT, "BVH4 node store exceeds 4 GB");
+    }
+    auto blob_ref = [&](uint32_t c) -> uint32_t {
+        if (c & PSY_CHILD_LEAF_BIT) return c;  // leaves and PSY_NONE
+        return ((std::min(s->nodes[c].n_keys, 8u) - 1u) << NODE2_KC_SHIFT) | unit_off[c];
+    };
     // flattened path records for the trace kernel's instance entry (dscene.cuh PATH_*)
     std::vector<uint4> path_recs(paths.size() * 2);
     std::vector<PsyXform> path_static(paths.size() * 2);
@@ -804,8 +815,10 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
         // shading class of a triangle hit on this path (k_trace_pool files finished rays by it)
         uint32_t sh_kind = in.shader_index == PSY_NONE ? (uint32_t)PSY_SHADER_EMIT : s->shaders[in.shader_index].kind;
         uint32_t cls = sh_kind == PSY_SHADER_LAMBERT ? SHADE_LAMBERT : (sh_kind == PSY_SHADER_GGX ? SHADE_GGX : SHADE_EMIT);
+        // r0.w: the BVH root of a mesh / assembly path as a blob reference (k_trace_pool); r1.x stays the ABI's (k_trace)
+        const uint32_t root2 = (kind == PATH_MESH || kind == PATH_ASSEMBLY) ? blob_ref(r1.x) : 0u;
         path_recs[2 * i] = make_uint4(kind | (own << 3) | (cls << PREC_CLS_SHIFT) | (dpaths[i].xf_count << 8), dpaths[i].xf_base,
-                                      dpaths[i].child_base, in.id);
+                                      dpaths[i].child_base, root2);
         path_recs[2 * i + 1] = r1;
         path_static[2 * i] = paths[i].keys.size() == 1 ? psyh::to_abi(paths[i].keys[0]) : psyh::to_abi(HXf());
         path_static[2 * i + 1] = path_inv[i];
@@ -894,6 +907,25 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
                 dm.vert_base, dm.tv_base);
         }
     }
+    // the node blob, built on the device from the ABI arrays just uploaded
+    {
+        DevBuf doff;
+        cudaError_t e_ = sc->node_blob.alloc((size_t)blob_units * 16);
+        if (e_ == cudaSuccess) e_ = doff.upload(unit_off.data(), unit_off.size(), st);
+        if (e_ != cudaSuccess) {
+            delete sc;
+            return fail(PSY_ERR_CUDA, std::string("node blob: ") + cudaGetErrorString(e_));
+        }
+        if (s->n_nodes)
+            k_build_node_blob<<<(s->n_nodes + 255) / 256, 256, 0, st>>>(sc->nodes.as<uint4>(), sc->motion.as<float4>(),
+                                                                      doff.as<uint32_t>(), s->n_nodes,
+                                                                      sc->node_blob.as<uint4>());
+        e_ = cudaStreamSynchronize(st);  // doff dies here
+        if (e_ != cudaSuccess) {
+            delete sc;
+            return fail(PSY_ERR_CUDA, std::string("node blob build: ") + cudaGetErrorString(e_));
+        }
+    }
     cudaError_t e = cudaStreamSynchronize(st);  // the staging vectors above die at return
     if (e != cudaSuccess) {
         delete sc;
@@ -903,11 +935,10 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
     DScene& d = sc->d;
     d.nodes = sc->nodes.as<uint4>();
     d.nodes_tex = 0;
-    d.motion_tex = 0;
     {
-        // Linear texture objects over the node and motion-key arrays, when they fit the device's 1D linear texture
-        // limit (16-byte texels); larger scenes leave them 0 and k_trace_pool loads through the LSU pipe instead.
-        // PSY_NODE_TEX=0 / PSY_MOTION_TEX=0 switch them off for A/B measurements.
+        // A linear texture object over the node blob, when it fits the device's 1D linear texture limit (16-byte
+        // texels); a larger scene leaves it 0 and k_trace_pool loads through the LSU pipe instead.
+        // PSY_NODE_TEX=0 switches it off for A/B measurements.
         int max_texels = 0;
         CK(cudaDeviceGetAttribute(&max_texels, cudaDevAttrMaxTexture1DLinearWidth, ctx->device));
         auto env_on = [](const char* name) {
@@ -916,26 +947,15 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
         };
         cudaTextureDesc td{};
         td.readMode = cudaReadModeElementType;
-        if (PSY_POOL_NODE_TEX && env_on("PSY_NODE_TEX") && s->n_nodes && (uint64_t)s->n_nodes * 8 <= (uint64_t)max_texels) {
+        if (PSY_POOL_NODE_TEX && env_on("PSY_NODE_TEX") && s->n_nodes && blob_units <= (uint64_t)max_texels) {
             cudaResourceDesc rd{};
             rd.resType = cudaResourceTypeLinear;
-            rd.res.linear.devPtr = sc->nodes.p;
+            rd.res.linear.devPtr = sc->node_blob.p;
             rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
-            rd.res.linear.sizeInBytes = (size_t)s->n_nodes * sizeof(PsyBvh4Node);
+            rd.res.linear.sizeInBytes = (size_t)blob_units * 16;
             cudaTextureObject_t tex = 0;
             CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
             d.nodes_tex = tex;
-        }
-        if (PSY_POOL_MOTION_TEX && env_on("PSY_MOTION_TEX") && s->n_motion_bounds &&
-            (uint64_t)s->n_motion_bounds * 6 <= (uint64_t)max_texels) {
-            cudaResourceDesc md{};
-            md.resType = cudaResourceTypeLinear;
-            md.res.linear.devPtr = sc->motion.p;
-            md.res.linear.desc = cudaCreateChannelDesc<float4>();
-            md.res.linear.sizeInBytes = (size_t)s->n_motion_bounds * sizeof(PsyBBox4);
-            cudaTextureObject_t mtex = 0;
-            CK(cudaCreateTextureObject(&mtex, &md, &td, nullptr));
-            d.motion_tex = mtex;
         }
     }
     d.motion_bounds = sc->motion.as<float4>();
@@ -960,7 +980,9 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
     d.path_inv = sc->path_inv.as<float4>();
     d.path_recs = sc->path_recs.as<uint4>();
     d.path_static = sc->path_static.as<float4>();
+    d.nodes2 = sc->node_blob.as<uint4>();
     d.root_bvh = s->assemblies[s->root_assembly].root;
+    d.root_bvh2 = blob_ref(d.root_bvh);
     d.root_instance_base = s->assemblies[s->root_assembly].instance_base;
     d.root_assembly = s->root_assembly;
     d.n_paths = (uint32_t)dpaths.size();

@@ -75,10 +75,10 @@ int psyh_synth_displaced_grid(uint32_t quads_per_side, uint32_t n_vert_keys, uin
 
 int psyh_synth_instanced(uint32_t asset_quads, uint32_t n_assets, uint32_t n_clusters, uint32_t inst_per_cluster,
                          uint32_t lights_per_cluster, uint32_t cluster_xform_keys, uint32_t res_x, uint32_t res_y,
-                         uint32_t spp, uint32_t seed, void** out) {
+                         uint32_t spp, uint32_t seed, uint32_t motion_pct, void** out) {
     return guarded([&] {
         SceneIR s = synth_instanced(asset_quads, n_assets, n_clusters, inst_per_cluster, lights_per_cluster,
-                                    cluster_xform_keys, res_x, res_y, spp, seed);
+                                    cluster_xform_keys, res_x, res_y, spp, seed, motion_pct ? motion_pct : 100);
         auto* hs = new HostScene();
         hs->flat = flatten_scene(s);
         *out = hs;

@@ -245,7 +245,7 @@ SceneIR synth_displaced_grid(uint32_t q, uint32_t n_vert_keys, uint32_t n_xform_
 
 SceneIR synth_instanced(uint32_t asset_quads, uint32_t n_assets, uint32_t n_clusters, uint32_t inst_per_cluster,
                         uint32_t lights_per_cluster, uint32_t cluster_xform_keys, uint32_t res_x, uint32_t res_y,
-                        uint32_t spp, uint32_t seed) {
+                        uint32_t spp, uint32_t seed, uint32_t motion_pct) {
     SceneIR sc;
     sc.name = "$synth_instanced";
     sc.output_path = "synth_instanced.png";
@@ -333,8 +333,13 @@ SceneIR synth_instanced(uint32_t asset_quads, uint32_t n_assets, uint32_t n_clus
         in.data_index = c;
         float cx = ((float)(c % side) - 0.5f * (float)(side - 1)) * spacing + rng.range(-2.0f, 2.0f);
         float cy = ((float)(c / side) - 0.5f * (float)(side - 1)) * spacing + rng.range(-2.0f, 2.0f);
-        float ang0 = rng.range(0.0f, 6.28f), dang = rng.range(-0.15f, 0.15f);
-        V3 drift = v3(rng.range(-0.4f, 0.4f), rng.range(-0.4f, 0.4f), 0.0f);
+        // motion over the shutter: drift up to 0.4 units and up to 0.15 rad of rotation at motion_pct = 100.  That
+        // much collapses under the builder's 1.4x union rule (bvh_base.rs:119-132): every node of the root BVH gets
+        // one merged box.  BASELINE config 4 ("motion-blurred instanced scene": 2-key bounds on the root assembly's
+        // nodes) uses motion_pct = 1250: drift up to 5 units, rotation up to 0.6 rad.
+        const float mscale = (float)motion_pct / 100.0f;
+        float ang0 = rng.range(0.0f, 6.28f), dang = rng.range(-0.15f, 0.15f) * std::min(mscale, 4.0f);
+        V3 drift = v3(rng.range(-0.4f, 0.4f), rng.range(-0.4f, 0.4f), 0.0f) * mscale;
         for (uint32_t k = 0; k < cluster_xform_keys; ++k) {
             float f = cluster_xform_keys > 1 ? (float)k / (float)(cluster_xform_keys - 1) : 0.0f;
             Xf l2w = affine_mul(translate(v3(cx, cy, 0.0f) + drift * f), rot_z(ang0 + dang * f));

@@ -103,7 +103,7 @@ def test_config_c5_non_finite_samples_are_the_references():
     guard either (renderer.rs:299-310).  The strict build must reproduce it at exactly that sample, and every
     other sample of both pixels bit for bit."""
     import bench
-    kw = dict(bench.WORKLOADS["C5"])
+    kw = dict(bench.WORKLOADS["C5r1"])  # the scene of BENCH_r01 / SCALE_r01, where the two pixels were reported
     scene = api.Scene.synth_instanced(**kw)
     r = api.Renderer(scene, strict=True)
     found = 0

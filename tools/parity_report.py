@@ -71,5 +71,8 @@ import bench
 kw = dict(bench.WORKLOADS["C5"])
 s = api.Scene.synth_instanced(**kw)
 image_row("C5 scene, 256x144 crop of the 4K frame at 64 spp", s, 64, kw["seed"], crop=(1792, 1008, 1792 + 255, 1008 + 143))
+kw = dict(bench.WORKLOADS["C5r1"])
+s = api.Scene.synth_instanced(**kw)
+image_row("C5 scene of round 1 (single-key nodes), same crop at 64 spp", s, 64, kw["seed"], crop=(1792, 1008, 1792 + 255, 1008 + 143))
 with open(out_path, "w") as f:
     json.dump({"what": "product build (libdevice) vs oracle (glibc), same seed / spp / sample sequences", "rows": rows}, f, indent=1)
