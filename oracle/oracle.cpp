@@ -1069,8 +1069,10 @@ struct LightPath {
                 float s4[4];
                 next_lds_samp(s4);
                 g_dbg_on = (px == g_dbg_px && py == g_dbg_py && sample_number == g_dbg_si);
+                sphere_lambert_debug() = g_dbg_on;
                 LightSample li = ls.sample_scene(s4[0], s4[1], s4[2], s4[3], wavelength, time, isect);
                 g_dbg_on = false;
+                sphere_lambert_debug() = false;
                 bool found_light = false;
                 ORC_DBG("  light kind %d pdf %.9g sel %.9g color (%.9g %.9g %.9g %.9g) pos (%.9g %.9g %.9g) nor (%.9g %.9g %.9g) dir (%.9g %.9g %.9g) s4 (%.9g %.9g %.9g)",
                         li.kind, (double)li.pdf, (double)li.selection_pdf, ORC_V4(li.color), ORC_V3(li.pos), ORC_V3(li.nor),
@@ -1466,6 +1468,22 @@ int oracle_camera_rays(const PsySceneDesc* d, uint32_t x0, uint32_t y0, uint32_t
 
 //---- unit-level entry points used to pin the restatement against the reference's own tests -------
 void oracle_set_strict_math(int on) { strict_math() = on != 0; }
+// sphere_lambert (surface_closure.rs:351-377) and the g / h terms it evaluates before branching
+float oracle_sphere_lambert(float nlcos, float rcos, float* g_h_nl_r) {
+    if (g_h_nl_r) {
+        float nlsin = std::sqrt(1.0f - (nlcos * nlcos));
+        float rsin2 = 1.0f - (rcos * rcos);
+        float rsin = std::sqrt(rsin2);
+        float ysin = rcos / nlsin;
+        float ycos2 = 1.0f - (ysin * ysin);
+        float ycos = std::sqrt(ycos2);
+        g_h_nl_r[0] = (-2.0f * nlsin * rcos * ycos) + H_PI - m_asinf(ysin) + (ysin * ycos);
+        g_h_nl_r[1] = nlcos * ((ycos * std::sqrt(rsin2 - ycos2)) + (rsin2 * m_asinf(ycos / rsin)));
+        g_h_nl_r[2] = m_acosf(nlcos);
+        g_h_nl_r[3] = m_acosf(rcos);
+    }
+    return sphere_lambert(nlcos, rcos);
+}
 double oracle_det_f64(int fn, double x) {
     return fn == 0 ? psy_det_sin(x) : fn == 1 ? psy_det_cos(x) : fn == 2 ? psy_det_acos(x) : fn == 3 ? psy_det_asin(x) : psy_det_log(x);
 }

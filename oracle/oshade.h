@@ -7,6 +7,7 @@
 //   src/shading/surface_closure.rs:57-155,281-633,714-719
 //   src/light/sphere_light.rs:51-192, rectangle_light.rs:52-243, distant_disk_light.rs:59-85
 #pragma once
+#include <cstdio>
 #include "osample.h"
 
 #define MENG_TABLE_QUAL static const
@@ -310,6 +311,10 @@ inline void closure_sample(const Closure& cl, V3 inc, V3 nor, V3 nor_g, float u,
     }
 }
 
+inline bool& sphere_lambert_debug() {
+    static bool on = false;
+    return on;
+}
 inline float sphere_lambert(float nlcos, float rcos) {
     float nlsin = std::sqrt(1.0f - (nlcos * nlcos));
     float rsin2 = 1.0f - (rcos * rcos);
@@ -321,6 +326,10 @@ inline float sphere_lambert(float nlcos, float rcos) {
     float h = nlcos * ((ycos * std::sqrt(rsin2 - ycos2)) + (rsin2 * m_asinf(ycos / rsin)));
     float nl = m_acosf(nlcos);
     float r = m_acosf(rcos);
+    if (sphere_lambert_debug())
+        std::fprintf(stderr, "[oracle dbg]       sphere_lambert nlcos %.9g rcos %.9g nl %.9g r %.9g  nl-(H_PI-r) %.3g  ysin %.9g ycos2 %.3g g %.9g h %.9g\n",
+                     (double)nlcos, (double)rcos, (double)nl, (double)r, (double)nl - ((double)H_PI - (double)r), (double)ysin,
+                     (double)ycos2, (double)g, (double)h);
     if (nl < (H_PI - r)) return nlcos * rsin2;
     if (nl < H_PI) return (nlcos * rsin2) + g - h;
     if (nl < (H_PI + r)) return (g + h) * INV_PI;

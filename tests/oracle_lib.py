@@ -79,6 +79,8 @@ def load():
     lib.oracle_xyz_from_spectral.argtypes = [F, f32, F]
     lib.oracle_xyz_from_spectral.restype = None
     lib.oracle_tri_intersect.argtypes = [F, F, f32, F, F]
+    lib.oracle_sphere_lambert.argtypes = [f32, f32, F]
+    lib.oracle_sphere_lambert.restype = f32
     lib.oracle_set_strict_math.argtypes = [C.c_int]
     lib.oracle_set_strict_math.restype = None
     lib.oracle_set_debug.argtypes = [u32, u32, u32]

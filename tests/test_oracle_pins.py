@@ -247,3 +247,30 @@ def test_spectral_roundtrip_and_white_furnace():
         acc += np.array(list(xyz))
     acc /= n
     assert np.allclose(acc, [0.35, 0.45, 0.2], rtol=0.08, atol=0.01), acc
+
+
+def test_sphere_lambert_boundary_is_where_the_references_nan_comes_from():
+    """The two non-finite pixels of round 1's 4K frame (BENCH_r01 `e2e.non_finite_pixels: 2`), root-caused.
+
+    `sphere_lambert` (surface_closure.rs:351-377) evaluates `ysin = rcos / nlsin; ycos = (1 - ysin^2).sqrt()` and the
+    g / h terms BEFORE it picks a case from `nl = acos(nlcos)`, `r = acos(rcos)`.  On the boundary between the fully
+    visible and the partially occluded case (nl = pi/2 - r) rounding makes ysin > 1, so g and h are NaN; whether the
+    NaN is returned hangs on the last bit of the two acos results.  LightTree::select (light_tree.rs:146-170) adds
+    the children's estimates without a guard, and neither the integrator nor the film (renderer.rs:299-310) has
+    one, so the NaN reaches the pixel.  Inputs below: pixel (1087, 1757), sample 161 of that frame (profiles/
+    r2_find_nan.txt): glibc keeps the child on the finite side by one ulp, CUDA's acosf does not — the product build
+    shows a NaN there, the oracle does not, and with the shared deterministic libm (strict mode) both agree."""
+    lib = O.load()
+    out = (C.c_float * 4)()
+    v = lib.oracle_sphere_lambert(0.563733935, 0.825956464, out)
+    g, h, nl, r = list(out)
+    assert np.isnan(g) and np.isnan(h)                      # the terms of the partially occluded case are NaN here ...
+    margin = np.float32(nl) - (np.float32(np.pi / 2) - np.float32(r))
+    assert abs(margin) <= 1.2e-7                            # ... one ulp from the case boundary
+    assert np.isfinite(v) == bool(margin < 0)               # and the result is finite only on the near side of it
+    # inputs on the same boundary where glibc's acos lands on the far side: the reference's formula returns NaN
+    # (this is what pixel (1566, 495) sample 210 of that frame hit on the CPU and the GPU alike)
+    for nlcos, rcos in [(0.42701658606529236, 0.9042438268661499), (0.46583878993988037, 0.8848696351051331),
+                        (0.8665500283241272, 0.4990902245044708)]:
+        assert np.isnan(lib.oracle_sphere_lambert(nlcos, rcos, out))
+        assert abs(np.float32(out[2]) - (np.float32(np.pi / 2) - np.float32(out[3]))) <= 2.4e-7
