@@ -223,6 +223,9 @@ def main():
                     help="path-pool size (paths in flight per GPU); 0 = the library's default: the whole image up to "
                          "64 Mi paths, at least ~6 buckets per GPU when tiled across GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--static-deal", action="store_true",
+                    help="N > 1: deal the buckets to the ranks by sample count instead of letting them pull (A/B)")
+    ap.add_argument("--buckets-per-gpu", type=int, default=0, help="N > 1: buckets per GPU (0 = the library's 12)")
     ap.add_argument("--no-c3", action="store_true",
                     help="skip the extra leg on BASELINE config 2 (10 M-triangle mesh, 4+4 motion keys: every BVH node a "
                          "motion node)")
@@ -247,8 +250,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the render core has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    wq_key = 0
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # the ranks pull buckets from a shared counter; its name is a fresh random key rank 0 hands out
+        k = torch.randint(1, 2 ** 31 - 1, (1,), dtype=torch.int64, device="cuda")
+        dist.broadcast(k, src=0)
+        wq_key = 0 if args.static_deal else int(k.item())
 
     name = args.workload
     kw = WORKLOADS[name]
@@ -258,7 +266,8 @@ def main():
     spp, seed = kw["spp"], kw["seed"]
     # what psy_render_image / _shard choose when max_samples_per_bucket is 0 (default_pool in psy_cuda.cu)
     total_samples = kw["res"][0] * kw["res"][1] * spp
-    pool_paths = args.pool or min(64 << 20, max(2 << 20, total_samples // (6 * world) if world > 1 else total_samples))
+    pool_paths = args.pool or min(64 << 20, max(2 << 20, total_samples // ((args.buckets_per_gpu or 12) * world)
+                                                if world > 1 else total_samples))
     scene, build_s = build_scene(name)
     t0 = time.time()
     r = api.Renderer(scene, device=local_rank)
@@ -279,7 +288,8 @@ def main():
         torch.cuda.synchronize()
 
     def step():
-        st = r.render_shard(rank, world, max_samples_per_bucket=args.pool) if world > 1 else \
+        st = r.render_shard(rank, world, max_samples_per_bucket=args.pool, work_queue_key=wq_key,
+                            buckets_per_gpu=args.buckets_per_gpu) if world > 1 else \
             r.render(max_samples_per_bucket=args.pool, device_resident_only=True)[1]
         if world > 1:
             dist.reduce(image_t, dst=0, op=dist.ReduceOp.SUM)  # tiles are disjoint, the rest is zero
@@ -339,7 +349,8 @@ def main():
         if world == 1:
             img_, st_ = rr.render(max_samples_per_bucket=args.pool)   # D2H: the finished image
         else:
-            st_ = rr.render_shard(rank, world, max_samples_per_bucket=args.pool)
+            st_ = rr.render_shard(rank, world, max_samples_per_bucket=args.pool, work_queue_key=wq_key,
+                                  buckets_per_gpu=args.buckets_per_gpu)
             ptr_, n_ = rr.device_image()
 
             class _W:
@@ -420,6 +431,8 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD_DESC[name], "resolution": [rx, ry], "spp": spp, "seed": seed,
                            "paths_in_flight": pool_paths, "parallelism": f"tiles x{world}",
+                           "tile_assignment": ("n/a" if world == 1 else "static deal by sample count" if not wq_key else
+                                               "ranks pull buckets from a shared-memory counter, largest first"),
                            "l2": "working set (path pool %d MB + scene) exceeds the 126 MB L2" % (pool_paths * 390 >> 20)},
                 "msamples_s": msamples, "rays_per_step": rays / args.steps, "samples_per_step": samples_per_step,
                 "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,

@@ -301,6 +301,7 @@ typedef struct PsyStats {
     uint64_t motion_node_visits; /* node visits that lerped two keys (counters) */
     uint64_t samples;           /* w*h*spp */
     uint64_t kernel_launches;   /* number of kernels this call launched */
+    uint64_t buckets;           /* buckets this call rendered (with several GPUs: how the work was shared) */
 } PsyStats;
 
 typedef struct PsyRenderParams {
@@ -318,6 +319,10 @@ typedef struct PsyRenderParams {
                                      swap compaction (src/renderer.rs:286-310): the image then depends on the bucket
                                      list exactly as the reference's does, so max_samples_per_bucket is the reference's
                                      `--spb` (0 = its default 4096) and a bucket holds at most 65536 paths (src/ray.rs:7) */
+    uint32_t buckets_per_gpu;     /* image shared between GPUs, max_samples_per_bucket == 0: buckets per GPU (0 = 12) */
+    uint32_t work_queue_key;      /* psy_render_image_shard: non-zero = the ranks of this node pull their buckets from
+                                     a counter in POSIX shared memory named by this key (any value all ranks agree on,
+                                     fresh per job) instead of being dealt a fixed share */
 } PsyRenderParams;
 
 typedef void (*psy_bucket_cb)(void* user, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
@@ -333,7 +338,10 @@ int32_t psy_abi_version(void);
 #define PSY_BUILD_STRICT_MATH 1u
 uint32_t psy_build_flags(void);
 
-/* device_ids == NULL -> device 0.  One context per process per GPU set. */
+/* device_ids == NULL -> device 0.  One context per process per GPU set.  With n_devices > 1 the context drives all of
+ * them from this process: scenes are replicated, psy_render_image shares the buckets between the GPUs (one host thread
+ * each, pulling from a common counter) and gathers the tiles onto the first device with NCCL (ncclCommInitAll here,
+ * one grouped ncclReduce per frame); psy_trace_rays / psy_render_bucket use the first device. */
 int32_t psy_init(const int* device_ids, int n_devices, PsyContext** out);
 int32_t psy_shutdown(PsyContext* ctx);
 
@@ -357,12 +365,23 @@ int32_t psy_render_bucket_samples(PsyScene* scene, uint32_t x, uint32_t y, uint3
 int32_t psy_render_image(PsyScene* scene, const PsyRenderParams* params, float* xyz_out, PsyStats* stats,
                          psy_bucket_cb on_bucket, void* user);
 
-/* Multi-process helpers (one process per GPU; tiles are rows of the Hilbert-ordered tile list).
- * Renders only tiles t with t % world == rank into a zero-initialised device image that the caller can
- * fetch as a device pointer for the NCCL gather. */
+/* One process per GPU (torchrun): renders this rank's share of the bucket list into a zero-initialised device image
+ * that the caller gathers with a collective (psy_device_image gives the pointer).  With params->work_queue_key the ranks
+ * pull buckets from a shared counter (largest buckets first) until the list is empty; without it the buckets are dealt
+ * by sample count, largest first, each to the rank with the least so far, the same on every rank.  Every rank must
+ * call it once per frame with the same arguments. */
 int32_t psy_render_image_shard(PsyScene* scene, const PsyRenderParams* params, uint32_t rank, uint32_t world,
                                PsyStats* stats);
 int32_t psy_device_image(PsyScene* scene, void** dev_ptr, size_t* n_floats);
+
+/* The work counter behind work_queue_key, usable on its own by a host that schedules buckets itself (the reference's
+ * Renderer::render, src/renderer.rs:138-180, with psy_render_bucket as the body of render_job): every process of the
+ * node that opens the same key shares 64 counters, one per frame in flight; psy_work_queue_pull returns 0, 1, 2, ...
+ * across all of them.  Frames must be used in increasing order and at most 32 apart between processes. */
+typedef struct PsyWorkQueue PsyWorkQueue;
+int32_t psy_work_queue_open(uint32_t key, PsyWorkQueue** out);
+int32_t psy_work_queue_pull(PsyWorkQueue* q, uint64_t frame, uint64_t* index);
+int32_t psy_work_queue_close(PsyWorkQueue* q);
 int32_t psy_scene_stream(PsyScene* scene, void** cuda_stream);
 int32_t psy_fetch_image(PsyScene* scene, float* xyz_out);
 

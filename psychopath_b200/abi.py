@@ -130,13 +130,14 @@ class PsyStats(C.Structure):
                 ("ray_generation_time", C.c_double), ("sample_writing_time", C.c_double),
                 ("total_time", C.c_double), ("ray_count", C.c_uint64), ("accel_node_visits", C.c_uint64),
                 ("tri_tests", C.c_uint64), ("instance_visits", C.c_uint64), ("motion_node_visits", C.c_uint64),
-                ("samples", C.c_uint64), ("kernel_launches", C.c_uint64)]
+                ("samples", C.c_uint64), ("kernel_launches", C.c_uint64), ("buckets", C.c_uint64)]
 
 
 class PsyRenderParams(C.Structure):
     _fields_ = [("crop_enabled", u32), ("crop_x1", u32), ("crop_y1", u32), ("crop_x2", u32), ("crop_y2", u32),
                 ("spp", u32), ("seed_override_enabled", u32), ("seed", u32), ("max_samples_per_bucket", u32),
-                ("collect_counters", u32), ("device_resident_only", u32), ("strict_film_order", u32)]
+                ("collect_counters", u32), ("device_resident_only", u32), ("strict_film_order", u32),
+                ("buckets_per_gpu", u32), ("work_queue_key", u32)]
 
 
 BUCKET_CB = C.CFUNCTYPE(None, C.c_void_p, u32, u32, u32, u32, C.POINTER(f32))
@@ -160,6 +161,7 @@ CUDA_SYMBOLS = [
     "psy_last_error", "psy_abi_version", "psy_build_flags", "psy_init", "psy_shutdown", "psy_scene_create", "psy_scene_destroy",
     "psy_trace_rays", "psy_render_bucket", "psy_render_bucket_samples", "psy_render_image",
     "psy_render_image_shard", "psy_device_image", "psy_scene_stream", "psy_fetch_image", "psy_last_trace_timing",
+    "psy_work_queue_open", "psy_work_queue_pull", "psy_work_queue_close",
 ]
 
 
@@ -211,6 +213,9 @@ def load_cuda(path=None):
     lib.psy_scene_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     lib.psy_fetch_image.argtypes = [C.c_void_p, C.c_void_p]
     lib.psy_last_trace_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    lib.psy_work_queue_open.argtypes = [u32, C.POINTER(C.c_void_p)]
+    lib.psy_work_queue_pull.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.psy_work_queue_close.argtypes = [C.c_void_p]
     for name in CUDA_SYMBOLS:
         if name not in ("psy_last_error", "psy_build_flags"):
             getattr(lib, name).restype = C.c_int32

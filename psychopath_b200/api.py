@@ -130,11 +130,13 @@ _ctx = {}
 
 
 def _context(device, strict=False):
+    """device: a CUDA device index, or a tuple of them (one context driving several GPUs from this process)."""
     lib = cuda_lib(strict)
     if (device, strict) not in _ctx:
         ctx = C.c_void_p()
-        ids = (C.c_int * 1)(device)
-        rc = lib.psy_init(ids, 1, C.byref(ctx))
+        devs = tuple(device) if isinstance(device, (tuple, list)) else (device,)
+        ids = (C.c_int * len(devs))(*devs)
+        rc = lib.psy_init(ids, len(devs), C.byref(ctx))
         if rc != 0:
             raise PsyError(f"psy_init failed ({rc}): {lib.psy_last_error().decode()}")
         _ctx[(device, strict)] = ctx
@@ -149,6 +151,10 @@ class DeviceScene:
     """The scene uploaded to one GPU (PsyScene*)."""
 
     def __init__(self, scene, device=0, strict=False):
+        """device: one CUDA device index, or a tuple of indices: the scene is then replicated on all of them and
+        render() shares the image's buckets between them (gathered onto the first with NCCL)."""
+        if isinstance(device, list):
+            device = tuple(device)
         self.scene = scene
         self.strict = bool(strict)
         self.lib = cuda_lib(self.strict)
@@ -206,9 +212,12 @@ class Renderer(Tracer):
     def output_file(self):
         return self.scene.output_file
 
-    def _params(self, max_samples_per_bucket, crop, spp, seed, counters, resident, strict_film=False):
+    def _params(self, max_samples_per_bucket, crop, spp, seed, counters, resident, strict_film=False,
+                buckets_per_gpu=0, work_queue_key=0):
         p = abi.PsyRenderParams()
         p.strict_film_order = 1 if strict_film else 0
+        p.buckets_per_gpu = int(buckets_per_gpu or 0)
+        p.work_queue_key = int(work_queue_key or 0) & 0xFFFFFFFF
         if crop is not None:
             p.crop_enabled = 1
             p.crop_x1, p.crop_y1, p.crop_x2, p.crop_y2 = [int(c) for c in crop]
@@ -222,13 +231,15 @@ class Renderer(Tracer):
         return p
 
     def render(self, max_samples_per_bucket=0, crop=None, thread_count=None, do_blender_output=False, spp=None,
-               seed=None, counters=False, on_bucket=None, device_resident_only=False, strict_film=False):
+               seed=None, counters=False, on_bucket=None, device_resident_only=False, strict_film=False,
+               buckets_per_gpu=0):
         """Returns (image, stats): image is float32 (res_y, res_x, 3) XYZ, row 0 = top (None when
         device_resident_only).  thread_count is accepted for signature parity and ignored (the GPU is the
         worker pool).  do_blender_output=True streams every finished bucket to stdout in the reference's
         protocol (renderer.rs:312-346) unless the caller installs its own on_bucket.
         strict_film=True adds the samples to the film in the reference's path order (PsyRenderParams)."""
-        p = self._params(max_samples_per_bucket, crop, spp, seed, counters, device_resident_only, strict_film)
+        p = self._params(max_samples_per_bucket, crop, spp, seed, counters, device_resident_only, strict_film,
+                         buckets_per_gpu)
         rx, ry = self.resolution
         img = None if device_resident_only else np.zeros((ry, rx, 3), dtype=np.float32)
         st = abi.PsyStats()
@@ -271,8 +282,12 @@ class Renderer(Tracer):
             sys.stdout.flush()
         return sink
 
-    def render_shard(self, rank, world, max_samples_per_bucket=0, spp=None, seed=None):
-        p = self._params(max_samples_per_bucket, None, spp, seed, False, True)
+    def render_shard(self, rank, world, max_samples_per_bucket=0, spp=None, seed=None, work_queue_key=0,
+                     buckets_per_gpu=0):
+        """One process per GPU: renders this rank's share of the buckets into the device image.  work_queue_key
+        (the same non-zero value on every rank of the node, fresh per job) makes the ranks pull buckets from a shared
+        counter; 0 deals them by sample count."""
+        p = self._params(max_samples_per_bucket, None, spp, seed, False, True, False, buckets_per_gpu, work_queue_key)
         st = abi.PsyStats()
         self._check(self.lib.psy_render_image_shard(self._s, C.byref(p), rank, world, C.byref(st)),
                     "psy_render_image_shard")

@@ -1,12 +1,22 @@
 // psy_cuda.cu — implementation of the C ABI in include/psy_cuda.h: scene upload, the wavefront
 // driver and the probe-ray entry.  Everything that computes runs in the CUDA kernels of
 // kernels.cuh; there is no CPU fallback (psy_init fails without a device).
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <nccl.h>  // types and enums only: the library is bound at run time (NcclApi below)
+#include <sys/mman.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../host/hmath.h"
@@ -81,12 +91,99 @@ struct PoolCache {
     uint32_t trace_blocks = 0;
 };
 
+// NCCL, bound with dlopen so that the library loads (and one-GPU rendering works) on a machine without it.
+// Used by contexts that drive several GPUs: the end-of-frame gather of the per-GPU tiles onto the first device.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err) {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) {
+            err = std::string("cannot load NCCL: ") + dlerror();
+            return false;
+        }
+        auto sym = [&](const char* n) { return dlsym(handle, n); };
+        CommInitAll = reinterpret_cast<decltype(CommInitAll)>(sym("ncclCommInitAll"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(sym("ncclCommDestroy"));
+        Reduce = reinterpret_cast<decltype(Reduce)>(sym("ncclReduce"));
+        GroupStart = reinterpret_cast<decltype(GroupStart)>(sym("ncclGroupStart"));
+        GroupEnd = reinterpret_cast<decltype(GroupEnd)>(sym("ncclGroupEnd"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));
+        if (!CommInitAll || !CommDestroy || !Reduce || !GroupStart || !GroupEnd || !GetErrorString) {
+            err = "libnccl.so.2 lacks a required symbol";
+            return false;
+        }
+        return true;
+    }
+};
+
+// Work counter shared by the processes of one node (one process per GPU): the ranks PULL buckets from it instead of
+// being dealt a fixed share, so a rank whose tiles are cheap (sky) takes more of them.  A POSIX shared-memory
+// object of 64 counters, one per frame in flight (frame f uses slot f % 64 and clears slot (f + 32) % 64: the
+// per-frame collective that gathers the tiles keeps the ranks less than 32 frames apart).
+struct ShmQueue {
+    struct Layout {
+        std::atomic<uint64_t> next[64];
+    };
+    Layout* mem = nullptr;
+    int fd = -1;
+    std::string name;
+    bool open(uint32_t key, std::string& err) {
+        char buf[64];
+        std::snprintf(buf, sizeof(buf), "/psy_wq_%08x", key);
+        name = buf;
+        fd = shm_open(name.c_str(), O_CREAT | O_RDWR, 0600);
+        if (fd < 0 || ftruncate(fd, sizeof(Layout)) != 0) {
+            err = "shm_open / ftruncate failed for " + name;
+            return false;
+        }
+        void* m = mmap(nullptr, sizeof(Layout), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (m == MAP_FAILED) {
+            err = "mmap failed for " + name;
+            return false;
+        }
+        mem = static_cast<Layout*>(m);  // (a new object is zero-filled)
+        return true;
+    }
+    void begin_frame(uint64_t frame) { mem->next[(frame + 32) % 64].store(0, std::memory_order_relaxed); }
+    uint64_t pull(uint64_t frame) { return mem->next[frame % 64].fetch_add(1, std::memory_order_relaxed); }
+    ~ShmQueue() {
+        if (mem) munmap(mem, sizeof(Layout));
+        if (fd >= 0) close(fd);
+        if (!name.empty()) shm_unlink(name.c_str());  // the mapping of the other ranks stays valid
+    }
+};
+
 struct PsyContext {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     std::mutex cache_mu;
     PoolCache cache;
+    // a context over several GPUs: this is the first device's; the others follow (psy_init with n_devices > 1)
+    std::vector<PsyContext*> peers;
+    std::vector<ncclComm_t> comms;  // comms[i]: device i of {this, peers...}
+    NcclApi nccl;
+    // process-per-GPU sharding (psy_render_image_shard): frames rendered so far, the shared work counter
+    uint64_t shard_frame = 0;
+    uint32_t wq_key = 0;
+    std::unique_ptr<ShmQueue> wq;
+    ~PsyContext() {
+        for (ncclComm_t c : comms)
+            if (c) nccl.CommDestroy(c);
+        for (PsyContext* p : peers) {
+            cudaSetDevice(p->device);
+            if (p->stream) cudaStreamDestroy(p->stream);
+            delete p;
+        }
+    }
 };
 
 struct PsyScene {
@@ -113,6 +210,8 @@ struct PsyScene {
     double last_trace_ms = 0.0;
     uint64_t last_trace_launches = 0;
     std::mutex mu;
+    // the copies of the scene on the other GPUs of a multi-GPU context (empty otherwise)
+    std::vector<PsyScene*> replicas;
     ~PsyScene() {
         if (d.nodes_tex) cudaDestroyTextureObject((cudaTextureObject_t)d.nodes_tex);
         for (auto e : events) cudaEventDestroy(e);
@@ -337,10 +436,15 @@ int32_t ensure_counts(PsyScene* sc, size_t n_buckets) {
     return PSY_OK;
 }
 
+// (nullptr when the driver refuses another event: the callers then skip the time stamp, cudaEventRecord(nullptr)
+// fails without side effects and sum_ms ignores pairs it cannot measure)
 cudaEvent_t next_event(PsyScene* sc) {
     if (sc->events_used == sc->events.size()) {
-        cudaEvent_t e;
-        cudaEventCreate(&e);
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
         sc->events.push_back(e);
     }
     return sc->events[sc->events_used++];
@@ -373,7 +477,7 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
     auto stamp = [&](std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* v, bool begin) {
         if (!ev) return;
         cudaEvent_t e = next_event(sc);
-        cudaEventRecord(e, st);
+        if (e) cudaEventRecord(e, st);
         if (begin)
             v->push_back({e, nullptr});
         else
@@ -480,7 +584,7 @@ double sum_ms(const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v) {
     double t = 0.0;
     for (auto& p : v) {
         float ms = 0.0f;
-        if (p.second && cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) t += ms;
+        if (p.first && p.second && cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) t += ms;
     }
     return t;
 }
@@ -520,8 +624,33 @@ std::vector<Bucket> make_buckets(uint32_t width, uint32_t height, uint32_t start
     return jobs;
 }
 
-int32_t render_buckets(PsyScene* sc, const std::vector<Bucket>& jobs, bool counters, PsyStats* stats, float* host_out,
-                       psy_bucket_cb cb, void* user, bool strict_film = false) {
+// Where a render takes its buckets from: the whole list in order (one GPU), or a counter shared with the other GPUs
+// of the job — threads of this process (std::atomic) or processes of this node (ShmQueue) — from which every GPU
+// pulls the next bucket when it is about to run dry.
+struct JobFeed {
+    std::function<int64_t()> next;  // index into the job list, or -1 when the list is exhausted
+    int max_in_flight = 0;          // buckets enqueued ahead of the GPU; 0 = no limit (static list)
+};
+
+JobFeed feed_all(size_t n_jobs, std::shared_ptr<size_t> pos = std::make_shared<size_t>(0)) {
+    JobFeed f;
+    f.next = [n_jobs, pos]() -> int64_t { return *pos < n_jobs ? (int64_t)(*pos)++ : -1; };
+    return f;
+}
+
+// after an aborted render the byte columns may hold stale classes / survivor marks: clear them before the next one
+void reset_after_error(PsyScene* sc) {
+    cudaStreamSynchronize(sc->ctx->stream);
+    cudaGetLastError();
+    if (sc->pool_cap) {
+        cudaMemsetAsync(sc->pool_cls.p, 0xFF, sc->pool_cap + 16, sc->ctx->stream);
+        cudaMemsetAsync(sc->pool_alive.p, 0xFF, sc->pool_cap + 16, sc->ctx->stream);
+        cudaStreamSynchronize(sc->ctx->stream);
+    }
+}
+
+int32_t render_buckets_impl(PsyScene* sc, const std::vector<Bucket>& jobs, JobFeed& feed, bool counters, PsyStats* stats,
+                            float* host_out, psy_bucket_cb cb, void* user, bool strict_film, std::mutex* cb_mu) {
     cudaStream_t st = sc->ctx->stream;
     auto t0 = std::chrono::steady_clock::now();
     size_t max_n = 0;
@@ -545,17 +674,38 @@ int32_t render_buckets(PsyScene* sc, const std::vector<Bucket>& jobs, bool count
     StageEvents ev;
     uint64_t launches = 0;
     std::vector<float> cb_buf;
-    for (size_t j = 0; j < jobs.size(); ++j) {
-        const Bucket& b = jobs[j];
-        rc = enqueue_bucket(sc, b, j, sc->image.as<float>(), sc->res_x, 0, 0, nullptr, counters, &ev, &launches, strict_film);
+    std::vector<size_t> mine;          // the buckets this GPU rendered, in the order it took them
+    std::vector<cudaEvent_t> done_ev;  // (pulling feeds only) bucket k has left the GPU
+    for (;;) {
+        if (feed.max_in_flight > 0 && (int)mine.size() >= feed.max_in_flight) {
+            // do not hoard: the next bucket is taken only when the GPU has at most max_in_flight - 1 left to do
+            cudaEvent_t e = done_ev[mine.size() - (size_t)feed.max_in_flight];
+            if (e) CK(cudaEventSynchronize(e));
+        }
+        const int64_t j = feed.next();
+        if (j < 0) break;
+        const Bucket& b = jobs[(size_t)j];
+        rc = enqueue_bucket(sc, b, mine.size(), sc->image.as<float>(), sc->res_x, 0, 0, nullptr, counters, &ev, &launches,
+                            strict_film);
         if (rc) return rc;
+        mine.push_back((size_t)j);
+        if (feed.max_in_flight > 0) {
+            cudaEvent_t e = next_event(sc);
+            if (e) CK(cudaEventRecord(e, st));
+            done_ev.push_back(e);
+        }
         if (cb) {
             // Blender-style streaming: hand the finished bucket to the caller (renderer.rs:312-346)
             cb_buf.resize((size_t)b.w * b.h * 3);
             CK(cudaMemcpy2DAsync(cb_buf.data(), (size_t)b.w * 12, sc->image.as<float>() + ((size_t)b.y * sc->res_x + b.x) * 3,
                                  (size_t)sc->res_x * 12, (size_t)b.w * 12, b.h, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            cb(user, b.x, b.y, b.x + b.w, b.y + b.h, cb_buf.data());
+            if (cb_mu) {
+                std::lock_guard<std::mutex> g(*cb_mu);
+                cb(user, b.x, b.y, b.x + b.w, b.y + b.h, cb_buf.data());
+            } else {
+                cb(user, b.x, b.y, b.x + b.w, b.y + b.h, cb_buf.data());
+            }
         }
     }
     if (host_out)
@@ -563,12 +713,12 @@ int32_t render_buckets(PsyScene* sc, const std::vector<Bucket>& jobs, bool count
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
 
-    std::vector<uint32_t> counts(jobs.size() * COUNT_SLOTS);
-    if (!jobs.empty()) CK(cudaMemcpy(counts.data(), sc->counts.p, counts.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> counts(mine.size() * COUNT_SLOTS);
+    if (!mine.empty()) CK(cudaMemcpy(counts.data(), sc->counts.p, counts.size() * 4, cudaMemcpyDeviceToHost));
     uint64_t rays = 0, samples = 0;
-    for (size_t j = 0; j < jobs.size(); ++j) {
-        for (int w = 0; w < WAVES; ++w) rays += counts[j * COUNT_SLOTS + w];
-        samples += (uint64_t)jobs[j].w * jobs[j].h * jobs[j].spp;
+    for (size_t k = 0; k < mine.size(); ++k) {
+        for (int w = 0; w < WAVES; ++w) rays += counts[k * COUNT_SLOTS + w];
+        samples += (uint64_t)jobs[mine[k]].w * jobs[mine[k]].h * jobs[mine[k]].spp;
     }
     TraceCounters tc{};
     if (counters) CK(cudaMemcpy(&tc, sc->counters.p, sizeof(tc), cudaMemcpyDeviceToHost));
@@ -588,8 +738,20 @@ int32_t render_buckets(PsyScene* sc, const std::vector<Bucket>& jobs, bool count
         stats->motion_node_visits = tc.motion_node_visits;
         stats->samples = samples;
         stats->kernel_launches = launches;
+        stats->buckets = mine.size();
     }
     return PSY_OK;
+}
+
+int32_t render_buckets(PsyScene* sc, const std::vector<Bucket>& jobs, JobFeed& feed, bool counters, PsyStats* stats,
+                       float* host_out, psy_bucket_cb cb, void* user, bool strict_film = false, std::mutex* cb_mu = nullptr) {
+    int32_t rc = render_buckets_impl(sc, jobs, feed, counters, stats, host_out, cb, user, strict_film, cb_mu);
+    if (rc) {
+        const std::string msg = g_err;
+        reset_after_error(sc);
+        g_err = msg;
+    }
+    return rc;
 }
 
 }  // namespace
@@ -600,21 +762,12 @@ const char* psy_last_error(void) { return g_err.c_str(); }
 int32_t psy_abi_version(void) { return PSY_ABI_VERSION; }
 uint32_t psy_build_flags(void) { return (PSY_STRICT ? PSY_BUILD_STRICT_MATH : 0u); }
 
-int32_t psy_init(const int* device_ids, int n_devices, PsyContext** out) {
-    if (!out) return fail(PSY_ERR_INVALID, "psy_init: out is null");
-    if (n_devices > 1)
-        return fail(PSY_ERR_INVALID, "one context drives one GPU: launch one process per GPU (torchrun) and shard tiles");
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0)
-        return fail(PSY_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) +
-                                           " (this library has no CPU fallback)");
-    int dev = (device_ids && n_devices == 1) ? device_ids[0] : 0;
-    if (dev < 0 || dev >= count) return fail(PSY_ERR_INVALID, "device id out of range");
+// One device of a context: stream + the constant-memory tables (per device)
+static int32_t init_device(int dev, std::unique_ptr<PsyContext>& out) {
     CK(cudaSetDevice(dev));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, dev));
-    PsyContext* c = new PsyContext();
+    std::unique_ptr<PsyContext> c(new PsyContext());
     c->device = dev;
     c->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -667,7 +820,50 @@ int32_t psy_init(const int* device_ids, int n_devices, PsyContext** out) {
     CK(cudaMemcpyToSymbol(c_meng_grid, MENG_GRID, sizeof(MENG_GRID)));
     CK(cudaMemcpyToSymbol(c_meng_uv, MENG_UV, sizeof(MENG_UV)));
     CK(cudaMemcpyToSymbol(c_meng_mat, MENG_MAT_XY_TO_UV, sizeof(MENG_MAT_XY_TO_UV)));
-    *out = c;
+    out = std::move(c);
+    return PSY_OK;
+}
+
+int32_t psy_init(const int* device_ids, int n_devices, PsyContext** out) {
+    if (!out) return fail(PSY_ERR_INVALID, "psy_init: out is null");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(PSY_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                           " (this library has no CPU fallback)");
+    std::vector<int> ids;
+    if (device_ids && n_devices >= 1)
+        ids.assign(device_ids, device_ids + n_devices);
+    else
+        ids.push_back(0);
+    for (size_t i = 0; i < ids.size(); ++i) {
+        if (ids[i] < 0 || ids[i] >= count) return fail(PSY_ERR_INVALID, "device id out of range");
+        for (size_t j = 0; j < i; ++j)
+            if (ids[j] == ids[i]) return fail(PSY_ERR_INVALID, "device listed twice");
+    }
+    std::unique_ptr<PsyContext> c;
+    int32_t rc = init_device(ids[0], c);
+    if (rc) return rc;
+    for (size_t i = 1; i < ids.size(); ++i) {
+        std::unique_ptr<PsyContext> p;
+        rc = init_device(ids[i], p);
+        if (rc) return rc;  // (c's destructor releases the peers made so far)
+        c->peers.push_back(p.release());
+    }
+    if (ids.size() > 1) {
+        // several GPUs in one process: their tiles are gathered with NCCL at the end of a frame (renderer.rs:76-191 is
+        // the seam: one worker per GPU instead of one per CPU thread)
+        std::string err;
+        if (!c->nccl.load(err)) return fail(PSY_ERR_CUDA, err);
+        c->comms.assign(ids.size(), nullptr);
+        ncclResult_t nr = c->nccl.CommInitAll(c->comms.data(), (int)ids.size(), ids.data());
+        if (nr != ncclSuccess) {
+            c->comms.clear();
+            return fail(PSY_ERR_CUDA, std::string("ncclCommInitAll: ") + c->nccl.GetErrorString(nr));
+        }
+    }
+    CK(cudaSetDevice(ids[0]));
+    *out = c.release();
     return PSY_OK;
 }
 
@@ -675,14 +871,12 @@ int32_t psy_shutdown(PsyContext* ctx) {
     if (!ctx) return PSY_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    delete ctx;  // peers, communicators, work queue
     return PSY_OK;
 }
 
-int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out) {
-    if (!ctx || !out) return fail(PSY_ERR_INVALID, "psy_scene_create: null argument");
-    int32_t rc = validate(s);
-    if (rc) return rc;
+static int32_t scene_create_one(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out) {
+    int32_t rc = PSY_OK;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
 
@@ -1020,12 +1214,40 @@ int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out)
     return PSY_OK;
 }
 
-int32_t psy_scene_destroy(PsyScene* scene) {
-    if (!scene) return PSY_OK;
+static void scene_destroy_one(PsyScene* scene) {
     cudaSetDevice(scene->ctx->device);
     cudaStreamSynchronize(scene->ctx->stream);
     donate_pool(scene);
     delete scene;
+}
+
+int32_t psy_scene_create(PsyContext* ctx, const PsySceneDesc* s, PsyScene** out) {
+    if (!ctx || !out) return fail(PSY_ERR_INVALID, "psy_scene_create: null argument");
+    int32_t rc = validate(s);
+    if (rc) return rc;
+    PsyScene* first = nullptr;
+    rc = scene_create_one(ctx, s, &first);
+    if (rc) return rc;
+    // a context over several GPUs replicates the scene (read-only) on each of them
+    for (PsyContext* peer : ctx->peers) {
+        PsyScene* r = nullptr;
+        rc = scene_create_one(peer, s, &r);
+        if (rc) {
+            for (PsyScene* x : first->replicas) scene_destroy_one(x);
+            scene_destroy_one(first);
+            return rc;
+        }
+        first->replicas.push_back(r);
+    }
+    cudaSetDevice(ctx->device);
+    *out = first;
+    return PSY_OK;
+}
+
+int32_t psy_scene_destroy(PsyScene* scene) {
+    if (!scene) return PSY_OK;
+    for (PsyScene* r : scene->replicas) scene_destroy_one(r);
+    scene_destroy_one(scene);
     return PSY_OK;
 }
 
@@ -1135,10 +1357,13 @@ int32_t psy_render_bucket_samples(PsyScene* sc, uint32_t x, uint32_t y, uint32_t
 // Paths in flight when the caller does not say (max_samples_per_bucket = 0).  Every wave of a bucket is one launch
 // of each kernel, and the later waves of a small bucket cannot fill 148 SMs x 20 warps x 80 rays: measured on the
 // C5 scene, 4 Mi paths in flight give 562 Mrays/s, 16 Mi 650, 64 Mi 679.  So: as many as the image has, up to
-// 64 Mi (25 GB of the 180 GB), but at least ~6 buckets per GPU when the image is shared between GPUs.
-static size_t default_pool(uint64_t total_samples, uint32_t world) {
+// 64 Mi (25 GB of the 180 GB).  When the image is shared between GPUs the buckets are the unit of load balancing:
+// `buckets_per_gpu` of them per GPU (default 12: the GPUs pull buckets as they finish, so the last one to finish is
+// at most one bucket late, ~4 % on average; smaller buckets would cost more than that in thin later waves).
+static size_t default_pool(uint64_t total_samples, uint32_t world, uint32_t buckets_per_gpu) {
     const uint64_t lo = 2ull << 20, hi = 64ull << 20;
-    uint64_t want = world > 1 ? total_samples / (6ull * world) : total_samples;
+    if (buckets_per_gpu == 0) buckets_per_gpu = 12;
+    uint64_t want = world > 1 ? total_samples / ((uint64_t)buckets_per_gpu * world) : total_samples;
     return (size_t)std::min(hi, std::max(lo, want));
 }
 
@@ -1155,8 +1380,19 @@ static int32_t image_jobs(PsyScene* sc, const PsyRenderParams* p, std::vector<Bu
         if (x2 < x1 || y2 < y1) return fail(PSY_ERR_INVALID, "crop rectangle is inverted");
         width = x2 - x1 + 1, height = y2 - y1 + 1, sx = x1, sy = y1;
     }
-    size_t spb = (p && p->max_samples_per_bucket) ? p->max_samples_per_bucket
-                                                  : default_pool((uint64_t)width * height * spp, world);
+    size_t spb = (p && p->max_samples_per_bucket)
+                     ? p->max_samples_per_bucket
+                     : default_pool((uint64_t)width * height * spp, world, p ? p->buckets_per_gpu : 0);
+    if (!(p && p->max_samples_per_bucket)) {
+        // ... and no more than the device has room for (~400 bytes per path incl. queues; a pool already allocated counts)
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t fit = std::max(sc->pool_cap, (size_t)((double)free_b * 0.8 / 400.0));
+            spb = std::min(spb, std::max(fit, (size_t)1 << 16));
+        } else {
+            cudaGetLastError();
+        }
+    }
     // the film order of the reference depends on its bucket list: strict renders use the reference's default --spb
     if (p && p->strict_film_order && !p->max_samples_per_bucket) spb = 4096;
     // a caller that wants every finished bucket (Blender's progressive display) gets buckets of a viewable size
@@ -1165,50 +1401,191 @@ static int32_t image_jobs(PsyScene* sc, const PsyRenderParams* p, std::vector<Bu
     return PSY_OK;
 }
 
+// Shared bucket lists are handed out largest first (stable: Hilbert order among equals), so that the partial
+// buckets of the image border — the small change — are what the GPUs even out with at the end of the frame.
+static std::vector<size_t> largest_first(const std::vector<Bucket>& all) {
+    std::vector<size_t> order(all.size());
+    for (size_t j = 0; j < all.size(); ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+        return (uint64_t)all[a].w * all[a].h * all[a].spp > (uint64_t)all[b].w * all[b].h * all[b].spp;
+    });
+    return order;
+}
+
+static void add_stats(PsyStats* total, const PsyStats& s) {
+    total->trace_time = std::max(total->trace_time, s.trace_time);
+    total->initial_ray_generation_time = std::max(total->initial_ray_generation_time, s.initial_ray_generation_time);
+    total->ray_generation_time = std::max(total->ray_generation_time, s.ray_generation_time);
+    total->sample_writing_time = std::max(total->sample_writing_time, s.sample_writing_time);
+    total->ray_count += s.ray_count;
+    total->accel_node_visits += s.accel_node_visits;
+    total->tri_tests += s.tri_tests;
+    total->instance_visits += s.instance_visits;
+    total->motion_node_visits += s.motion_node_visits;
+    total->samples += s.samples;
+    total->kernel_launches += s.kernel_launches;
+    total->buckets += s.buckets;
+}
+
+// Renderer::render over the GPUs of one context (renderer.rs:76-191 with one worker per GPU): a host thread per GPU
+// pulls buckets from a shared counter and renders them into its GPU's zero-initialised image; the disjoint tiles are
+// then summed onto the first GPU with one grouped ncclReduce over NVLink, and fetched from there.
+static int32_t render_image_multi(PsyScene* sc, const PsyRenderParams* p, float* xyz_out, PsyStats* stats, psy_bucket_cb cb,
+                                  void* user) {
+    PsyContext* ctx = sc->ctx;
+    std::vector<PsyScene*> devs{sc};
+    devs.insert(devs.end(), sc->replicas.begin(), sc->replicas.end());
+    const uint32_t world = (uint32_t)devs.size();
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<Bucket> jobs;
+    int32_t rc = image_jobs(sc, p, jobs, world, cb != nullptr);
+    if (rc) return rc;
+    const std::vector<size_t> order = largest_first(jobs);
+    std::atomic<size_t> next{0};
+    std::vector<int32_t> rcs(world, PSY_OK);
+    std::vector<std::string> errs(world);
+    std::vector<PsyStats> sts(world);
+    std::mutex cb_mu;
+    const bool counters = p && p->collect_counters, strict = p && p->strict_film_order;
+    std::vector<std::thread> workers;
+    for (uint32_t i = 0; i < world; ++i) {
+        workers.emplace_back([&, i]() {
+            PsyScene* d = devs[i];
+            std::lock_guard<std::mutex> g(d->mu);
+            auto run = [&]() -> int32_t {
+                CK(cudaSetDevice(d->ctx->device));
+                if (!d->image.p) CK(d->image.alloc((size_t)d->res_x * d->res_y * 3 * sizeof(float)));
+                CK(cudaMemsetAsync(d->image.p, 0, d->image.bytes, d->ctx->stream));
+                JobFeed feed;
+                feed.max_in_flight = 2;
+                feed.next = [&]() -> int64_t {
+                    const size_t k = next.fetch_add(1);
+                    return k < order.size() ? (int64_t)order[k] : -1;
+                };
+                return render_buckets(d, jobs, feed, counters, &sts[i], nullptr, cb, user, strict, &cb_mu);
+            };
+            rcs[i] = run();
+            if (rcs[i]) errs[i] = g_err;
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (uint32_t i = 0; i < world; ++i)
+        if (rcs[i]) return fail(rcs[i], "GPU " + std::to_string(devs[i]->ctx->device) + ": " + errs[i]);
+    // gather: the images are disjoint and zero elsewhere, so the sum onto device 0 is the image
+    const size_t n_floats = (size_t)sc->res_x * sc->res_y * 3;
+    ncclResult_t nr = ctx->nccl.GroupStart();
+    for (uint32_t i = 0; i < world && nr == ncclSuccess; ++i)
+        nr = ctx->nccl.Reduce(devs[i]->image.p, devs[i]->image.p, n_floats, ncclFloat, ncclSum, 0, ctx->comms[i],
+                              devs[i]->ctx->stream);
+    ncclResult_t ne = ctx->nccl.GroupEnd();
+    if (nr == ncclSuccess) nr = ne;
+    if (nr != ncclSuccess) return fail(PSY_ERR_CUDA, std::string("ncclReduce: ") + ctx->nccl.GetErrorString(nr));
+    for (uint32_t i = world; i-- > 0;) {
+        CK(cudaSetDevice(devs[i]->ctx->device));
+        if (i == 0 && xyz_out && !(p && p->device_resident_only))
+            CK(cudaMemcpyAsync(xyz_out, sc->image.p, sc->image.bytes, cudaMemcpyDeviceToHost, sc->ctx->stream));
+        CK(cudaStreamSynchronize(devs[i]->ctx->stream));
+    }
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        for (uint32_t i = 0; i < world; ++i) add_stats(stats, sts[i]);
+        stats->total_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    sc->last_trace_ms = 0.0, sc->last_trace_launches = 0;
+    for (uint32_t i = 0; i < world; ++i) {
+        sc->last_trace_ms = std::max(sc->last_trace_ms, devs[i]->last_trace_ms);
+        if (i) sc->last_trace_launches += devs[i]->last_trace_launches;
+    }
+    return PSY_OK;
+}
+
 int32_t psy_render_image(PsyScene* sc, const PsyRenderParams* p, float* xyz_out, PsyStats* stats, psy_bucket_cb cb,
                          void* user) {
     if (!sc) return fail(PSY_ERR_INVALID, "null scene");
     bool resident = p && p->device_resident_only;
     if (!xyz_out && !resident) return fail(PSY_ERR_INVALID, "xyz_out is null and device_resident_only is not set");
+    if (!sc->replicas.empty()) return render_image_multi(sc, p, xyz_out, stats, cb, user);
     std::lock_guard<std::mutex> g(sc->mu);
     CK(cudaSetDevice(sc->ctx->device));
     std::vector<Bucket> jobs;
     int32_t rc = image_jobs(sc, p, jobs, 1, cb != nullptr);
     if (rc) return rc;
     if (sc->image.p) CK(cudaMemsetAsync(sc->image.p, 0, sc->image.bytes, sc->ctx->stream));
-    return render_buckets(sc, jobs, p && p->collect_counters, stats, resident ? nullptr : xyz_out, cb, user,
+    JobFeed feed = feed_all(jobs.size());
+    return render_buckets(sc, jobs, feed, p && p->collect_counters, stats, resident ? nullptr : xyz_out, cb, user,
                           p && p->strict_film_order);
 }
 
 int32_t psy_render_image_shard(PsyScene* sc, const PsyRenderParams* p, uint32_t rank, uint32_t world, PsyStats* stats) {
     if (!sc || world == 0 || rank >= world) return fail(PSY_ERR_INVALID, "bad shard arguments");
+    if (!sc->replicas.empty()) return fail(PSY_ERR_INVALID, "psy_render_image_shard is the one-process-per-GPU entry");
     std::lock_guard<std::mutex> g(sc->mu);
     CK(cudaSetDevice(sc->ctx->device));
-    std::vector<Bucket> all, mine;
+    PsyContext* ctx = sc->ctx;
+    std::vector<Bucket> all;
     int32_t rc = image_jobs(sc, p, all, world);
     if (rc) return rc;
-    // Deal the buckets so that every rank gets about the same number of samples: largest first, each to the rank with
-    // the least so far (the buckets at the image border are partial; plain round-robin left ranks idle at 8 GPUs).
-    // Every rank computes the same assignment; a rank renders its buckets in Hilbert order.
-    {
-        std::vector<size_t> order(all.size());
-        for (size_t j = 0; j < all.size(); ++j) order[j] = j;
-        auto samples = [&](size_t j) { return (uint64_t)all[j].w * all[j].h * all[j].spp; };
-        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return samples(a) > samples(b); });
+    if (sc->image.p) CK(cudaMemsetAsync(sc->image.p, 0, sc->image.bytes, ctx->stream));
+    const std::vector<size_t> order = largest_first(all);
+    const uint64_t frame = ctx->shard_frame++;
+    JobFeed feed;
+    if (p && p->work_queue_key && world > 1) {
+        // The ranks of this node pull buckets from a counter in shared memory (every rank calls this function once per
+        // frame, with the same arguments, and gathers the tiles with a collective before the next frame).
+        if (!ctx->wq || ctx->wq_key != p->work_queue_key) {
+            std::string err;
+            std::unique_ptr<ShmQueue> q(new ShmQueue());
+            if (!q->open(p->work_queue_key, err)) return fail(PSY_ERR_INVALID, err);
+            ctx->wq = std::move(q);
+            ctx->wq_key = p->work_queue_key;
+        }
+        ShmQueue* q = ctx->wq.get();
+        q->begin_frame(frame);
+        feed.max_in_flight = 2;
+        feed.next = [q, frame, &order]() -> int64_t {
+            const uint64_t k = q->pull(frame);
+            return k < order.size() ? (int64_t)order[k] : -1;
+        };
+    } else {
+        // No shared counter: a fixed deal by sample count, largest first, each bucket to the rank with the least so far
+        // (every rank computes the same assignment); a rank renders its buckets in Hilbert order.
         std::vector<uint64_t> load(world, 0);
-        std::vector<size_t> my_idx;
+        auto mine = std::make_shared<std::vector<size_t>>();
         for (size_t j : order) {
             uint32_t r = 0;
             for (uint32_t k = 1; k < world; ++k)
                 if (load[k] < load[r]) r = k;
-            load[r] += samples(j);
-            if (r == rank) my_idx.push_back(j);
+            load[r] += (uint64_t)all[j].w * all[j].h * all[j].spp;
+            if (r == rank) mine->push_back(j);
         }
-        std::sort(my_idx.begin(), my_idx.end());
-        for (size_t j : my_idx) mine.push_back(all[j]);
+        std::sort(mine->begin(), mine->end());
+        auto pos = std::make_shared<size_t>(0);
+        feed.next = [mine, pos]() -> int64_t { return *pos < mine->size() ? (int64_t)(*mine)[(*pos)++] : -1; };
     }
-    if (sc->image.p) CK(cudaMemsetAsync(sc->image.p, 0, sc->image.bytes, sc->ctx->stream));
-    return render_buckets(sc, mine, p && p->collect_counters, stats, nullptr, nullptr, nullptr);
+    return render_buckets(sc, all, feed, p && p->collect_counters, stats, nullptr, nullptr, nullptr,
+                          p && p->strict_film_order);
+}
+
+// The shared work counter on its own (no GPU involved): for a host that schedules buckets itself, like the reference's
+// Renderer::render with psy_render_bucket as its render_job body, and for the CPU tests.
+int32_t psy_work_queue_open(uint32_t key, PsyWorkQueue** out) {
+    if (!out || key == 0) return fail(PSY_ERR_INVALID, "psy_work_queue_open: null argument or zero key");
+    std::unique_ptr<ShmQueue> q(new ShmQueue());
+    std::string err;
+    if (!q->open(key, err)) return fail(PSY_ERR_INVALID, err);
+    *out = reinterpret_cast<PsyWorkQueue*>(q.release());
+    return PSY_OK;
+}
+int32_t psy_work_queue_pull(PsyWorkQueue* q, uint64_t frame, uint64_t* index) {
+    if (!q || !index) return fail(PSY_ERR_INVALID, "psy_work_queue_pull: null argument");
+    ShmQueue* s = reinterpret_cast<ShmQueue*>(q);
+    s->begin_frame(frame);
+    *index = s->pull(frame);
+    return PSY_OK;
+}
+int32_t psy_work_queue_close(PsyWorkQueue* q) {
+    delete reinterpret_cast<ShmQueue*>(q);
+    return PSY_OK;
 }
 
 int32_t psy_device_image(PsyScene* sc, void** dev_ptr, size_t* n_floats) {

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -80,6 +81,9 @@ int main(int argc, char** argv) {
     bool has_input = false, stats = false, dev = false, serialized = false, use_stdin = false, has_crop = false;
     uint32_t spp = 0, spb = 0, crop[4] = {0, 0, 0, 0};
     int device = 0;
+    std::vector<int> devices;  // --gpus N / --device-list a,b,c (flags the GPU host adds)
+    bool counters = false;
+    std::string probe_in, probe_out;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto need = [&](int n) {
@@ -107,6 +111,27 @@ int main(int argc, char** argv) {
         } else if (a == "--device") {
             need(1);
             device = std::atoi(argv[++i]);
+        } else if (a == "--gpus") {
+            need(1);
+            int n = std::atoi(argv[++i]);
+            if (n < 1) die("Argument '--gpus' must be at least 1");
+            devices.clear();
+            for (int k = 0; k < n; ++k) devices.push_back(k);
+        } else if (a == "--device-list") {
+            need(1);
+            devices.clear();
+            std::stringstream ss(argv[++i]);
+            std::string tok;
+            while (std::getline(ss, tok, ',')) devices.push_back(std::atoi(tok.c_str()));
+            if (devices.empty()) die("Argument '--device-list' needs a comma-separated list of CUDA device indices");
+        } else if (a == "--counters") {
+            counters = true;
+        } else if (a == "--probe-rays") {
+            need(1);
+            probe_in = argv[++i];
+        } else if (a == "--probe-out") {
+            need(1);
+            probe_out = argv[++i];
         } else if (a == "--stats") {
             stats = true;
         } else if (a == "--dev") {
@@ -156,7 +181,10 @@ int main(int argc, char** argv) {
     if (!serialized) std::printf("\tParsed scene file in %.3fs\n", t.tick());
 
     PsyContext* ctx = nullptr;
-    if (psy_init(&device, 1, &ctx) != PSY_OK) die(std::string("psy_init: ") + psy_last_error());
+    if (devices.empty()) devices.push_back(device);
+    if (psy_init(devices.data(), (int)devices.size(), &ctx) != PSY_OK) die(std::string("psy_init: ") + psy_last_error());
+    std::string device_names;
+    for (size_t k = 0; k < devices.size(); ++k) device_names += (k ? "," : "") + std::to_string(devices[k]);
 
     for (uint32_t si = 0; si < n_scenes; ++si) {
         t.tick();
@@ -171,7 +199,30 @@ int main(int argc, char** argv) {
         PsyScene* scene = nullptr;
         if (psy_scene_create(ctx, desc, &scene) != PSY_OK) die(std::string("psy_scene_create: ") + psy_last_error());
         if (!serialized) std::printf("\tBuilt scene in %.3fs\n", t.tick());
-        if (!serialized) std::printf("Rendering scene on CUDA device %d...\n", device);
+        if (!probe_in.empty()) {
+            // --probe-rays FILE: trace a file of PsyRay records (36 bytes each: orig[3] dir[3] time max_t flags) through
+            // the scene instead of rendering it, and write the PsyHit records (32 bytes each) to --probe-out (default
+            // FILE.hits) — the closest-hit parity check of the north star from the command line
+            std::ifstream pf(probe_in, std::ios::binary);
+            if (!pf) die("Cannot open '" + probe_in + "'");
+            std::vector<char> raw((std::istreambuf_iterator<char>(pf)), std::istreambuf_iterator<char>());
+            if (raw.size() % sizeof(PsyRay) != 0) die("'" + probe_in + "' is not a whole number of 36-byte ray records");
+            const size_t n = raw.size() / sizeof(PsyRay);
+            std::vector<PsyHit> hits(n);
+            if (psy_trace_rays(scene, reinterpret_cast<const PsyRay*>(raw.data()), n, hits.data(), nullptr) != PSY_OK)
+                die(std::string("psy_trace_rays: ") + psy_last_error());
+            const std::string outp = probe_out.empty() ? probe_in + ".hits" : probe_out;
+            std::ofstream of(outp, std::ios::binary);
+            of.write(reinterpret_cast<const char*>(hits.data()), (std::streamsize)(n * sizeof(PsyHit)));
+            if (!of) die("Cannot write '" + outp + "'");
+            size_t n_hit = 0;
+            for (auto& h : hits) n_hit += (h.kind != PSY_HIT_MISS && h.kind != PSY_HIT_OCCLUDED) ? 1 : 0;
+            std::printf("Traced %zu probe rays (%zu hits) in %.3fs, wrote '%s'\n", n, n_hit, t.tick(), outp.c_str());
+            psy_scene_destroy(scene);
+            psyh_scene_free(hs);
+            continue;
+        }
+        if (!serialized) std::printf("Rendering scene on CUDA device%s %s...\n", devices.size() > 1 ? "s" : "", device_names.c_str());
 
         PsyRenderParams params;
         std::memset(&params, 0, sizeof(params));
@@ -182,7 +233,7 @@ int main(int argc, char** argv) {
         // (without --spb: 4 Mi-path buckets when Blender displays them as they arrive, else as large as the library
         // allows — the later waves of small buckets cannot fill the GPU)
         params.max_samples_per_bucket = spb ? spb : (serialized ? (4u << 20) : (64u << 20));
-        params.collect_counters = stats ? 1u : 0u;
+        params.collect_counters = (stats || counters) ? 1u : 0u;
         std::vector<float> image((size_t)desc->res_x * desc->res_y * 3);
         PsyStats rs;
         StreamState st;
@@ -211,6 +262,16 @@ int main(int argc, char** argv) {
             std::printf("\t\tInitial ray generation: %.3fs\n", rs.initial_ray_generation_time);
             std::printf("\t\tRay generation:         %.3fs\n", rs.ray_generation_time);
             std::printf("\t\tSample writing:         %.3fs\n", rs.sample_writing_time);
+            if (counters) {
+                // --counters: what the roofline is made of, per ray
+                const double rays = (double)std::max<uint64_t>(rs.ray_count, 1);
+                const double nn = rs.accel_node_visits / rays, nm = rs.motion_node_visits / rays, nt = rs.tri_tests / rays,
+                             ni = rs.instance_visits / rays;
+                std::printf("\t\tPer ray: %.2f node visits (%.2f with two time keys), %.2f triangle tests, %.2f instance entries\n",
+                            nn, nm, nt, ni);
+                std::printf("\t\tBuckets: %llu, kernel launches: %llu\n", (unsigned long long)rs.buckets,
+                            (unsigned long long)rs.kernel_launches);
+            }
 
             std::string out_path = psyh_output_path(hs);
             std::printf("Writing image to disk into '%s'...\n", out_path.c_str());

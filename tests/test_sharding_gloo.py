@@ -83,3 +83,47 @@ def test_two_rank_tile_gather(tmp_path):
     scene = api.Scene.from_psy_string(motion_instances_text())
     ref, _, _ = O.render_image(scene.desc, 2, 7, spb=256, threads=1)
     assert np.array_equal(img.reshape(ref.shape).astype(np.float32), ref)
+
+
+def _puller(key, frames, n_jobs, q, barrier):
+    sys.path.insert(0, REPO)
+    import ctypes as C
+    from psychopath_b200 import abi
+    lib = abi.load_cuda()
+    h = C.c_void_p()
+    assert lib.psy_work_queue_open(key, C.byref(h)) == 0
+    got = {}
+    for f in frames:
+        barrier.wait()  # the per-frame collective of the real thing (the tile gather) keeps the ranks in step
+        mine = []
+        while True:
+            idx = C.c_uint64()
+            assert lib.psy_work_queue_pull(h, f, C.byref(idx)) == 0
+            if idx.value >= n_jobs:
+                break
+            mine.append(idx.value)
+        got[f] = mine
+    q.put(got)
+    barrier.wait()
+    lib.psy_work_queue_close(h)
+
+
+def test_shared_work_counter_hands_every_bucket_to_exactly_one_process():
+    """The pull scheduler of the N > 1 path (psy_render_image_shard with work_queue_key): processes that open the same
+    key draw 0, 1, 2, ... from one shared-memory counter per frame — no bucket twice, none lost, over 70 frames
+    (more than the 64 counter slots, so slot reuse is covered).  The library is loaded without a GPU."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    key = (os.getpid() * 2654435761) & 0x7FFFFFFF or 1
+    n_jobs, frames = 37, list(range(70))
+    q = ctx.Queue()
+    barrier = ctx.Barrier(3)
+    procs = [ctx.Process(target=_puller, args=(key, frames, n_jobs, q, barrier)) for _ in range(3)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for f in frames:
+        drawn = sorted(i for r in results for i in r[f])
+        assert drawn == list(range(n_jobs)), f
