@@ -40,6 +40,9 @@ constexpr int POOL_WARPS = 4;             // warps per block
 #define PSY_POOL_MIN_BLOCKS 5
 #endif
 constexpr uint32_t POOL_WIN = 4;  // stack entries below the top that stay in shared memory
+#ifndef PSY_POOL_NODE_REPS
+#define PSY_POOL_NODE_REPS 1  // internal nodes a ray may take in one step (see the node step)
+#endif
 #ifndef PSY_POOL_RECYCLE
 #define PSY_POOL_RECYCLE 24  // finished rays / free slots that trigger their recycling (trace ms per C5 frame at
                              // 16 spp: 8 -> 377, 16 -> 362, 24 -> 354, 32 -> 378)
@@ -290,8 +293,21 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
         } else if (k == Q_NODE) {
             // ---- one internal node (bvh4.rs:118-166, bbox4.rs:63-97)
             if (act) {
+                uint32_t ref = ST(PF_TOP, r);
+                flags = ST(PF_FLAGS, r);
+                PSY_LOAD_SP()
+                const bool in_mesh = (flags & RF_IN_MESH) != 0u;
+                const uint32_t fo = in_mesh ? (uint32_t)PF_MOL : (uint32_t)PF_OL;
+                const V3 ol = mk3(STF(fo + 0, r), STF(fo + 1, r), STF(fo + 2, r));
+                const V3 di = mk3(STF(fo + 3, r), STF(fo + 4, r), STF(fo + 5, r));
+                const uint32_t space = in_mesh ? (flags >> RF_MSPACE_SHIFT) & 15u : (flags >> 1) & 15u;  // finite | octant << 1
+                const float max_t = STF(PF_MAXT, r);
+                // A ray whose nearest hit child is again an internal node takes that node in the same step (up to
+                // PSY_POOL_NODE_REPS in a row): its next fetch is issued as soon as the slab test is done, instead of
+                // after a trip through the queues.  Lanes whose next entry is a leaf (or nothing) sit the repeats out.
+#pragma unroll 1
+                for (int rep_i = 0;; ++rep_i) {
                 // blob reference (dscene.cuh): unit offset of the node, and how many time keys follow its header
-                const uint32_t ref = ST(PF_TOP, r);
                 const uint32_t unit = ref & NODE2_OFF_MASK, kc = ref >> NODE2_KC_SHIFT;
                 const uint4* np = S.nodes2 + unit;
                 // header and first key at once (for motion nodes the first key is replaced below; its memory is valid)
@@ -338,14 +354,6 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
 #undef PSY_LERP4
                     }
                 }
-                flags = ST(PF_FLAGS, r);
-                PSY_LOAD_SP()
-                const bool in_mesh = (flags & RF_IN_MESH) != 0u;
-                const uint32_t fo = in_mesh ? (uint32_t)PF_MOL : (uint32_t)PF_OL;
-                const V3 ol = mk3(STF(fo + 0, r), STF(fo + 1, r), STF(fo + 2, r));
-                const V3 di = mk3(STF(fo + 3, r), STF(fo + 4, r), STF(fo + 5, r));
-                const uint32_t space = in_mesh ? (flags >> RF_MSPACE_SHIFT) & 15u : (flags >> 1) & 15u;  // finite | octant << 1
-                const float max_t = STF(PF_MAXT, r);
                 if (kc == 7u) {
                     // 8 or more time keys: the count comes from the header (a dependent fetch, like the ABI layout)
                     uint32_t i1;
@@ -430,70 +438,77 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                     lo = sp > lo + POOL_WIN ? sp - POOL_WIN : lo;  // (the taken-back entry used a ring slot too)
                     if (hits) --sp;
                 }
+                if (rep_i + 1 >= PSY_POOL_NODE_REPS || (top & PSY_CHILD_LEAF_BIT)) break;  // (PSY_NONE has the leaf bit)
+                ref = top;
+                }
             }
         } else if (k == Q_TRI) {
-            // ---- one triangle of the leaf on top (triangle_mesh.rs:174-262)
+            // ---- the triangles of the leaf on top (triangle_mesh.rs:174-262): all of them (<= 3) in this step, in
+            // leaf order and against the running max_t like the reference's inner loop; the ray's constants and the
+            // mesh's local->world matrix are fetched once per leaf
             if (act) {
                 const uint32_t leaf = ST(PF_TOP, r);
-                const uint32_t ti = PSY_CHILD_LEAF_START(leaf), count = PSY_CHILD_LEAF_COUNT(leaf);
+                const uint32_t ti0 = PSY_CHILD_LEAF_START(leaf), count = PSY_CHILD_LEAF_COUNT(leaf);
                 const uint32_t nk = ST(PF_NK, r);
-                const float4* tv = S.tri_verts + (size_t)(ST(PF_TVBASE, r) + ti * 3u * nk);
+                const float4* tv = S.tri_verts + (size_t)(ST(PF_TVBASE, r) + ti0 * 3u * nk);
                 flags = ST(PF_FLAGS, r);
                 PSY_LOAD_SP()
-                top = count > 1u ? PSY_CHILD_LEAF(ti + 1u, count - 1u) : PSY_NONE;
-                if (count != 0u) {
-                    V3 p0, p1, p2;
-                    if (nk == 1u) {
-                        p0 = f4_xyz(__ldg(tv)), p1 = f4_xyz(__ldg(tv + 1)), p2 = f4_xyz(__ldg(tv + 2));
-                    } else {
-                        uint32_t i1;
-                        float a2;
-                        if (!lerp_slice_keys(nk, STF(PF_TIME, r), i1, a2)) {
-                            p0 = f4_xyz(__ldg(tv + i1));
-                            p1 = f4_xyz(__ldg(tv + nk + i1));
-                            p2 = f4_xyz(__ldg(tv + 2 * nk + i1));
-                        } else {
-                            p0 = lerp3(f4_xyz(__ldg(tv + i1)), f4_xyz(__ldg(tv + i1 + 1)), a2);
-                            p1 = lerp3(f4_xyz(__ldg(tv + nk + i1)), f4_xyz(__ldg(tv + nk + i1 + 1)), a2);
-                            p2 = lerp3(f4_xyz(__ldg(tv + 2 * nk + i1)), f4_xyz(__ldg(tv + 2 * nk + i1 + 1)), a2);
-                        }
+                top = PSY_NONE;
+                RayTriPre pre;
+                pre.xi = (int)((flags >> RF_PERM_SHIFT) & 3u);
+                pre.yi = (int)((flags >> (RF_PERM_SHIFT + 2)) & 3u);
+                pre.zi = (int)((flags >> (RF_PERM_SHIFT + 4)) & 3u);
+                const V3 op = mk3(__uint_as_float(rcb[0 * R + r]), __uint_as_float(rcb[1 * R + r]),
+                                  __uint_as_float(rcb[2 * R + r]));
+                pre.sx = __uint_as_float(rcb[3 * R + r]), pre.sy = __uint_as_float(rcb[4 * R + r]);
+                pre.sz = __uint_as_float(rcb[5 * R + r]);
+                const bool has_space = !(flags & RF_SPACE_EMPTY);
+                Xf ms = xf_identity();
+                if (has_space) {
+                    const uint32_t* m = msb + r;
+                    ms.X = mk3(__uint_as_float(m[0 * R]), __uint_as_float(m[1 * R]), __uint_as_float(m[2 * R]));
+                    ms.Y = mk3(__uint_as_float(m[3 * R]), __uint_as_float(m[4 * R]), __uint_as_float(m[5 * R]));
+                    ms.Z = mk3(__uint_as_float(m[6 * R]), __uint_as_float(m[7 * R]), __uint_as_float(m[8 * R]));
+                    ms.T = mk3(__uint_as_float(m[9 * R]), __uint_as_float(m[10 * R]), __uint_as_float(m[11 * R]));
+                }
+                uint32_t i1 = 0;
+                float a2 = 0.0f;
+                const bool blend = nk != 1u && lerp_slice_keys(nk, STF(PF_TIME, r), i1, a2);
+                float max_t = STF(PF_MAXT, r);
+                bool hit_any = false;
+#pragma unroll 1
+                for (uint32_t c = 0; c < count; ++c) {
+                    const float4* v = tv + (size_t)c * 3u * nk + i1;
+                    V3 p0 = f4_xyz(__ldg(v)), p1 = f4_xyz(__ldg(v + nk)), p2 = f4_xyz(__ldg(v + 2u * nk));
+                    if (blend) {
+                        p0 = lerp3(p0, f4_xyz(__ldg(v + 1)), a2);
+                        p1 = lerp3(p1, f4_xyz(__ldg(v + nk + 1)), a2);
+                        p2 = lerp3(p2, f4_xyz(__ldg(v + 2u * nk + 1)), a2);
                     }
-                    RayTriPre pre;
-                    pre.xi = (int)((flags >> RF_PERM_SHIFT) & 3u);
-                    pre.yi = (int)((flags >> (RF_PERM_SHIFT + 2)) & 3u);
-                    pre.zi = (int)((flags >> (RF_PERM_SHIFT + 4)) & 3u);
-                    const V3 op = mk3(__uint_as_float(rcb[0 * R + r]), __uint_as_float(rcb[1 * R + r]),
-                                      __uint_as_float(rcb[2 * R + r]));
-                    pre.sx = __uint_as_float(rcb[3 * R + r]), pre.sy = __uint_as_float(rcb[4 * R + r]);
-                    pre.sz = __uint_as_float(rcb[5 * R + r]);
-                    if (!(flags & RF_SPACE_EMPTY)) {
-                        const uint32_t* m = msb + r;
-                        Xf ms;
-                        ms.X = mk3(__uint_as_float(m[0 * R]), __uint_as_float(m[1 * R]), __uint_as_float(m[2 * R]));
-                        ms.Y = mk3(__uint_as_float(m[3 * R]), __uint_as_float(m[4 * R]), __uint_as_float(m[5 * R]));
-                        ms.Z = mk3(__uint_as_float(m[6 * R]), __uint_as_float(m[7 * R]), __uint_as_float(m[8 * R]));
-                        ms.T = mk3(__uint_as_float(m[9 * R]), __uint_as_float(m[10 * R]), __uint_as_float(m[11 * R]));
+                    if (has_space) {
                         p0 = xf_point(ms, p0), p1 = xf_point(ms, p1), p2 = xf_point(ms, p2);
                     } else {
                         p0 = permute3(p0, pre), p1 = permute3(p1, pre), p2 = permute3(p2, pre);
                     }
                     if (COUNT) cnt.tri_tests += 1;
                     float t, b0, b1, b2;
-                    if (tri_intersect_perm(op, pre, STF(PF_MAXT, r), p0, p1, p2, t, b0, b1, b2)) {
+                    if (tri_intersect_perm(op, pre, max_t, p0, p1, p2, t, b0, b1, b2)) {
                         if (flags & RF_OCCL) {
                             flags = (flags & ~RF_HIT_MASK) | ((uint32_t)PSY_HIT_OCCLUDED << RF_HIT_SHIFT);
-                            top = PSY_NONE, sp = 0, lo = 0;
-                        } else {
-                            const uint32_t mesh_path = ST(PF_MESH_PATH, r);
-                            ST(PF_MAXT, r) = __float_as_uint(t);
-                            flags = (flags & ~(RF_HIT_MASK | (3u << RF_HCLS_SHIFT))) |
-                                    ((uint32_t)PSY_HIT_TRIANGLE << RF_HIT_SHIFT) |
-                                    (((flags >> RF_MCLS_SHIFT) & 3u) << RF_HCLS_SHIFT);
-                            uint4* hp = reinterpret_cast<uint4*>(P.hits + ST(PF_SLOT, r));
-                            hp[0] = make_uint4(PSY_HIT_TRIANGLE, __float_as_uint(t), ti, mesh_path);
-                            hp[1] = make_uint4(__float_as_uint(b0), __float_as_uint(b1), __float_as_uint(b2), 0u);
+                            sp = 0, lo = 0;
+                            break;  // triangle_mesh.rs:247-250: the ray is done
                         }
+                        max_t = t;
+                        hit_any = true;
+                        uint4* hp = reinterpret_cast<uint4*>(P.hits + ST(PF_SLOT, r));
+                        hp[0] = make_uint4(PSY_HIT_TRIANGLE, __float_as_uint(t), ti0 + c, ST(PF_MESH_PATH, r));
+                        hp[1] = make_uint4(__float_as_uint(b0), __float_as_uint(b1), __float_as_uint(b2), 0u);
                     }
+                }
+                if (hit_any) {
+                    ST(PF_MAXT, r) = __float_as_uint(max_t);
+                    flags = (flags & ~(RF_HIT_MASK | (3u << RF_HCLS_SHIFT))) | ((uint32_t)PSY_HIT_TRIANGLE << RF_HIT_SHIFT) |
+                            (((flags >> RF_MCLS_SHIFT) & 3u) << RF_HCLS_SHIFT);
                 }
             }
         } else {

@@ -419,6 +419,7 @@ int32_t ensure_pool(PsyScene* sc, size_t n) {
         sc->pool_trace_blocks = (uint32_t)sc->ctx->sm_count * PSY_POOL_MIN_BLOCKS;
         CK(sc->trace_scratch.alloc((size_t)sc->pool_trace_blocks * POOL_WARPS * POOL_SCRATCH_WORDS_PER_WARP * 4));
         CK(cudaFuncSetAttribute(k_trace_pool<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POOL_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_trace_pool<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POOL_SMEM_BYTES));
     }
     sc->pool_cap = cap;
     return PSY_OK;
@@ -509,6 +510,13 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
         const char* e = getenv("PSY_TRACE_KERNEL");
         return !(e && std::string(e) == "warp");
     }();
+    // The visit counters come from the counting instantiation of the production kernel (k_trace_pool<true>: same
+    // traversal, four more per-lane adds); PSY_POOL_COUNT=0 takes them from k_trace<true> instead (A/B: both kernels
+    // visit exactly the same nodes / primitives per ray, tests/test_gpu_parity.py compares them).
+    static const bool pool_counting = [] {
+        const char* e = getenv("PSY_POOL_COUNT");
+        return pool_kernel && !(e && e[0] == '0');
+    }();
     for (int c = 0; c < SHADE_CLASSES; ++c) Q.q[c] = sc->queues.as<uint32_t>() + (size_t)c * sc->pool_cap;
     uint32_t* qcounts = sc->qcounts.as<uint32_t>() + bucket_index * COUNT_SLOTS * SHADE_CLASSES;
     // slot-ordered lists from the per-slot byte columns (dpartition.cuh)
@@ -517,12 +525,13 @@ int32_t enqueue_bucket(PsyScene* sc, const Bucket& b, size_t bucket_index, float
     for (int w = 0; w < WAVES; ++w) {
         Q.count = qcounts + w * SHADE_CLASSES;
         stamp(ev ? &ev->trace : nullptr, true);
-        // The visit counters (--stats, bench.py's roofline pass) are collected by the one-ray-per-lane kernel:
-        // both kernels visit exactly the same nodes / primitives per ray, and the counting build of
-        // k_trace_pool is not used (ptxas 12.9 drops the divergence guards of its warp votes).
         if (pool_kernel && !counters)
             k_trace_pool<false><<<sc->pool_trace_blocks, 32 * POOL_WARPS, POOL_SMEM_BYTES, st>>>(
                 sc->d, P, act[w & 1], counts + w, fetch + w, nullptr, Q, sc->trace_scratch.as<uint32_t>());
+        else if (counters && pool_counting)
+            k_trace_pool<true><<<sc->pool_trace_blocks, 32 * POOL_WARPS, POOL_SMEM_BYTES, st>>>(
+                sc->d, P, act[w & 1], counts + w, fetch + w, sc->counters.as<TraceCounters>(), Q,
+                sc->trace_scratch.as<uint32_t>());
         else if (counters)
             k_trace<true><<<trace_blocks, 128, 0, st>>>(sc->d, P, act[w & 1], counts + w, fetch + w,
                                                         sc->counters.as<TraceCounters>(), Q, tune);

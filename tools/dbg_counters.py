@@ -1,19 +1,17 @@
-"""Debug helper: renders a small image of a C5-like scene with and without counters (run under compute-sanitizer)."""
+"""Visit counters of the two counting kernels on the same scene: k_trace<true> (one ray per lane) and the counting
+instantiation of k_trace_pool (PSY_POOL_COUNT=1).  Run each in its own process:
+    python tools/dbg_counters.py            # k_trace<true>
+    PSY_POOL_COUNT=1 python tools/dbg_counters.py"""
 import os
 import sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
 import numpy as np
 from psychopath_b200 import api
-q = int(sys.argv[1])
-s = api.Scene.synth_instanced(asset_quads=q, n_assets=4, n_clusters=100, inst_per_cluster=10, lights_per_cluster=10,
-                              cluster_xform_keys=2, res=(int(sys.argv[2]), int(sys.argv[3])), spp=int(sys.argv[4]), seed=5)
+s = api.Scene.synth_instanced(asset_quads=200, n_assets=4, n_clusters=40, inst_per_cluster=8, lights_per_cluster=6,
+                              cluster_xform_keys=2, res=(480, 270), spp=8, seed=11, motion_pct=1250)
 r = api.Renderer(s)
-mode = sys.argv[5] if len(sys.argv) > 5 else "both"
-if mode != "nocount":
-    img, st = r.render(counters=True)
-    print("ok", st["ray_count"], st["accel_node_visits"], st["tri_tests"], st["instance_visits"])
-if mode != "count":
-    img2, st2 = r.render(counters=False)
-    print("plain", st2["ray_count"])
-if mode == "both":
-    print("same image:", np.array_equal(img, img2, equal_nan=True))
+a, sa = r.render()
+c, sc = r.render(counters=True)
+print("image equal:", np.array_equal(a, c, equal_nan=True), "rays", sa["ray_count"], sc["ray_count"], "nodes", sc["accel_node_visits"],
+      "motion", sc["motion_node_visits"], "tris", sc["tri_tests"], "inst", sc["instance_visits"])
