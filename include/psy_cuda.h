@@ -374,6 +374,25 @@ int32_t psy_render_image_shard(PsyScene* scene, const PsyRenderParams* params, u
                                PsyStats* stats);
 int32_t psy_device_image(PsyScene* scene, void** dev_ptr, size_t* n_floats);
 
+/* SURVEY.md N3 — the GPU build of a mesh BVH, behind a flag (`psychopath --gpu-build`, api.enable_gpu_build()).
+ * Replaces the ORDERING and TOPOLOGY half of BVHBase::from_objects (src/accel/bvh_base.rs:57-215): triangles sorted along
+ * a 63-bit Morton curve of their centroids at shutter time 0.5,
+ * binary radix tree over the sorted triangles (LBVH), subtrees of at most `tris_per_leaf` (<= 3) triangles as leaves.
+ * Host arrays in and out:
+ *   verts   n_verts * n_keys * 3 floats, the time keys of a vertex contiguous (PsySceneDesc.verts layout)
+ *   tri_idx 3 vertex indices per triangle
+ *   order   n_tris: the triangle that ends up at each position of the leaf-ordered list
+ *   left / right / axis   room for n_tris - 1 entries; *n_internal are written, one per internal node.  A child >= 0
+ *           is an internal node; a child < 0 is a leaf: code = ~child, positions [code >> 2, (code >> 2) + (code & 3))
+ *           of `order`
+ *   root    reference of the root in the same encoding (0, or a leaf when the mesh has <= tris_per_leaf triangles);
+ *   depth   depth of the deepest leaf (root = 0)
+ * The host derives time-sampled bounds, the 1.4x union rule and the BVH4 collapse from it exactly as for its SAH
+ * trees (psyh_set_mesh_topology_builder in libpsy_host.so takes this function's address). */
+int32_t psy_build_mesh_topology(PsyContext* ctx, const float* verts, uint32_t n_verts, uint32_t n_keys, const uint32_t* tri_idx,
+                                uint32_t n_tris, uint32_t tris_per_leaf, uint32_t* order, int32_t* left, int32_t* right,
+                                uint8_t* axis, uint32_t* n_internal, int32_t* root, uint32_t* depth);
+
 /* The work counter behind work_queue_key, usable on its own by a host that schedules buckets itself (the reference's
  * Renderer::render, src/renderer.rs:138-180, with psy_render_bucket as the body of render_job): every process of the
  * node that opens the same key shares 64 counters, one per frame in flight; psy_work_queue_pull returns 0, 1, 2, ...

@@ -161,7 +161,7 @@ CUDA_SYMBOLS = [
     "psy_last_error", "psy_abi_version", "psy_build_flags", "psy_init", "psy_shutdown", "psy_scene_create", "psy_scene_destroy",
     "psy_trace_rays", "psy_render_bucket", "psy_render_bucket_samples", "psy_render_image",
     "psy_render_image_shard", "psy_device_image", "psy_scene_stream", "psy_fetch_image", "psy_last_trace_timing",
-    "psy_work_queue_open", "psy_work_queue_pull", "psy_work_queue_close",
+    "psy_work_queue_open", "psy_work_queue_pull", "psy_work_queue_close", "psy_build_mesh_topology",
 ]
 
 
@@ -187,6 +187,10 @@ def load_host():
     lib.psyh_hilbert_d2xy.restype = None
     lib.psyh_bucket_list.argtypes = [u32] * 6 + [C.POINTER(u32), u32]
     lib.psyh_bucket_list.restype = u32
+    lib.psyh_set_mesh_topology_builder.argtypes = [C.c_void_p, C.c_void_p, u32]
+    lib.psyh_set_mesh_topology_builder.restype = None
+    lib.psyh_take_mesh_topology_seconds.argtypes = [C.POINTER(u32)]
+    lib.psyh_take_mesh_topology_seconds.restype = C.c_double
     return lib
 
 

@@ -43,6 +43,27 @@ class PsyError(RuntimeError):
     pass
 
 
+def enable_gpu_build(min_tris=1 << 20, device=0):
+    """meshes of at least `min_tris` triangles get their triangle order and BVH topology from the GPU
+    LBVH build (psy_build_mesh_topology) instead of the host's SAH builder; bounds and the BVH4 collapse stay as
+    they are.  Scenes built afterwards (Scene.from_* / synth_*) use it; disable_gpu_build() restores the SAH builder."""
+    lib = cuda_lib()
+    ctx = _context(device)
+    fn = C.cast(lib.psy_build_mesh_topology, C.c_void_p)
+    host_lib().psyh_set_mesh_topology_builder(fn, ctx, int(min_tris))
+
+
+def disable_gpu_build():
+    host_lib().psyh_set_mesh_topology_builder(None, None, 0)
+
+
+def gpu_build_seconds():
+    """(seconds inside the GPU builder, meshes it built) since the last call."""
+    n = C.c_uint32()
+    s = host_lib().psyh_take_mesh_topology_seconds(C.byref(n))
+    return s, n.value
+
+
 class Scene:
     """A parsed and built scene living in host memory (flat PsySceneDesc)."""
 

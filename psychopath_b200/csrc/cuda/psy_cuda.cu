@@ -21,6 +21,7 @@
 
 #include "../host/hmath.h"
 #include "kernels.cuh"
+#include "dbuild.cuh"
 
 #define MENG_TABLE_QUAL static const
 #include "../../../tables/meng_tables.inc"
@@ -1573,6 +1574,87 @@ int32_t psy_render_image_shard(PsyScene* sc, const PsyRenderParams* p, uint32_t 
     }
     return render_buckets(sc, all, feed, p && p->collect_counters, stats, nullptr, nullptr, nullptr,
                           p && p->strict_film_order);
+}
+
+// SURVEY.md N3 — LBVH topology of one mesh on the GPU (dbuild.cuh).  Host arrays in, host arrays out.
+int32_t psy_build_mesh_topology(PsyContext* ctx, const float* verts, uint32_t n_verts, uint32_t n_keys, const uint32_t* tri_idx,
+                                uint32_t n_tris, uint32_t tris_per_leaf, uint32_t* order, int32_t* left, int32_t* right,
+                                uint8_t* axis, uint32_t* n_internal, int32_t* root, uint32_t* depth) {
+    if (!ctx || !verts || !tri_idx || !order || !root || !depth || !n_internal || n_keys == 0 || tris_per_leaf == 0 ||
+        tris_per_leaf > 3)
+        return fail(PSY_ERR_INVALID, "psy_build_mesh_topology: bad argument");
+    if (n_tris == 0 || n_tris > (PSY_MAX_LEAF_START >> 2)) return fail(PSY_ERR_INVALID, "psy_build_mesh_topology: triangle count");
+    if (n_tris > tris_per_leaf && (!left || !right || !axis)) return fail(PSY_ERR_INVALID, "psy_build_mesh_topology: null output");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf dverts, didx, dcent, dbox, dkeys, dkeys2, dvals, dvals2, dtmp, dleft, dright, daxis, drng, dnpar, dlpar, dkeep, dnew,
+        dleft2, dright2, daxis2, ddepth;
+    CK(dverts.upload(verts, (size_t)n_verts * n_keys * 3, st));
+    CK(didx.upload(tri_idx, (size_t)n_tris * 3, st));
+    CK(dcent.alloc((size_t)n_tris * sizeof(float3)));
+    const uint32_t box_init[6] = {~0u, ~0u, ~0u, 0u, 0u, 0u};
+    CK(dbox.upload(box_init, 6, st));
+    CK(dkeys.alloc((size_t)n_tris * 8));
+    CK(dkeys2.alloc((size_t)n_tris * 8));
+    CK(dvals.alloc((size_t)n_tris * 4));
+    CK(dvals2.alloc((size_t)n_tris * 4));
+    const unsigned tb = (n_tris + 255) / 256;
+    k_lbvh_centroids<<<tb, 256, 0, st>>>(dverts.as<float>(), n_keys, didx.as<uint32_t>(), n_tris, dcent.as<float3>(),
+                                         dbox.as<uint32_t>());
+    k_lbvh_morton<<<tb, 256, 0, st>>>(dcent.as<float3>(), n_tris, dbox.as<uint32_t>(), dkeys.as<uint64_t>(), dvals.as<uint32_t>());
+    size_t tmp_bytes = 0, scan_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dkeys.as<uint64_t>(), dkeys2.as<uint64_t>(), dvals.as<uint32_t>(),
+                                       dvals2.as<uint32_t>(), (int)n_tris, 0, 63, st));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_tris, st));
+    CK(dtmp.alloc(std::max(tmp_bytes, scan_bytes)));
+    CK(cub::DeviceRadixSort::SortPairs(dtmp.p, tmp_bytes, dkeys.as<uint64_t>(), dkeys2.as<uint64_t>(), dvals.as<uint32_t>(),
+                                       dvals2.as<uint32_t>(), (int)n_tris, 0, 63, st));
+    *depth = 0;
+    *n_internal = 0;
+    if (n_tris > tris_per_leaf) {
+        const int n_nodes = (int)n_tris - 1;  // of the radix tree over single triangles
+        CK(dleft.alloc((size_t)n_nodes * 4));
+        CK(dright.alloc((size_t)n_nodes * 4));
+        CK(daxis.alloc((size_t)n_nodes));
+        CK(drng.alloc((size_t)n_nodes * sizeof(int2)));
+        CK(dnpar.alloc((size_t)n_nodes * 4));
+        CK(dlpar.alloc((size_t)n_tris * 4));
+        CK(dkeep.alloc((size_t)n_nodes * 4));
+        CK(dnew.alloc((size_t)n_nodes * 4));
+        CK(dleft2.alloc((size_t)n_nodes * 4));
+        CK(dright2.alloc((size_t)n_nodes * 4));
+        CK(daxis2.alloc((size_t)n_nodes));
+        CK(ddepth.alloc(4));
+        CK(cudaMemsetAsync(ddepth.p, 0, 4, st));
+        const unsigned nb = ((unsigned)n_nodes + 255) / 256;
+        k_lbvh_tree<<<nb, 256, 0, st>>>(dkeys2.as<uint64_t>(), (int)n_tris, dleft.as<int32_t>(), dright.as<int32_t>(),
+                                        daxis.as<uint8_t>(), drng.as<int2>(), dnpar.as<int32_t>(), dlpar.as<int32_t>());
+        k_lbvh_flag<<<nb, 256, 0, st>>>(drng.as<int2>(), n_nodes, (int)tris_per_leaf, dkeep.as<uint32_t>());
+        CK(cub::DeviceScan::ExclusiveSum(dtmp.p, scan_bytes, dkeep.as<uint32_t>(), dnew.as<uint32_t>(), n_nodes, st));
+        k_lbvh_emit<<<nb, 256, 0, st>>>(dleft.as<int32_t>(), dright.as<int32_t>(), daxis.as<uint8_t>(), drng.as<int2>(),
+                                        dkeep.as<uint32_t>(), dnew.as<uint32_t>(), n_nodes, dleft2.as<int32_t>(),
+                                        dright2.as<int32_t>(), daxis2.as<uint8_t>());
+        k_lbvh_depth<<<tb, 256, 0, st>>>(dnpar.as<int32_t>(), dlpar.as<int32_t>(), dkeep.as<uint32_t>(), (int)n_tris,
+                                         ddepth.as<uint32_t>());
+        CK(cudaGetLastError());
+        uint32_t last_keep = 0, last_new = 0;
+        CK(cudaMemcpyAsync(&last_keep, dkeep.as<uint32_t>() + (n_nodes - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&last_new, dnew.as<uint32_t>() + (n_nodes - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(depth, ddepth.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint32_t n_int = last_keep + last_new;  // (the root spans everything: it is kept, and is new node 0)
+        *n_internal = n_int;
+        CK(cudaMemcpyAsync(left, dleft2.p, (size_t)n_int * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(right, dright2.p, (size_t)n_int * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(axis, daxis2.p, (size_t)n_int, cudaMemcpyDeviceToHost, st));
+        *root = 0;
+    } else {
+        *root = ~(int32_t)((0u << 2) | n_tris);  // the whole mesh is one leaf
+    }
+    CK(cudaMemcpyAsync(order, dvals2.p, (size_t)n_tris * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return PSY_OK;
 }
 
 // The shared work counter on its own (no GPU involved): for a host that schedules buckets itself, like the reference's

@@ -12,9 +12,13 @@
 // planes are monotone), and large subtrees are built on several threads.
 #pragma once
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <deque>
 #include <memory>
 #include <mutex>
+#include <stdexcept>
 #include <thread>
 #include <vector>
 
@@ -35,6 +39,25 @@ struct ObjBoundsView {
 };
 
 inline uint64_t log2_64(uint64_t n) { return n == 0 ? 0 : (uint64_t)(63 - __builtin_clzll(n)); }
+
+// f(begin, end) over [0, n) on the host's cores (chunks of at least `grain` items)
+template <typename F>
+inline void parallel_for(size_t n, size_t grain, F f) {
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = std::min<size_t>(hw ? hw : 1, (n + grain - 1) / std::max<size_t>(grain, 1));
+    if (nt <= 1) {
+        f((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    size_t per = (n + nt - 1) / nt;
+    for (size_t t = 0; t < nt; ++t) {
+        size_t b = t * per, e = std::min(n, b + per);
+        if (b >= e) break;
+        th.emplace_back([=]() { f(b, e); });
+    }
+    for (auto& x : th) x.join();
+}
 
 // partition (src/algorithm.rs:44-81): same scan/swap sequence, predicate called once per element.
 template <typename T, typename P>
@@ -330,6 +353,126 @@ class BVHBaseBuilder {
     std::atomic<size_t> depth_{0};
 };
 
+// A binary tree whose topology comes from elsewhere (the GPU LBVH build): internal node i has children
+// left[i] / right[i] and a split axis.  A child >= 0 is an internal node; a child < 0 is a leaf: code = ~child holds
+// ids[code >> 2 .. (code >> 2) + (code & 3)) of the ALREADY ORDERED id list.
+struct Bvh2Topology {
+    uint32_t n_internal = 0;
+    const int32_t* left = nullptr;
+    const int32_t* right = nullptr;
+    const uint8_t* axis = nullptr;
+    int32_t root = 0;  // (>= 0 unless the tree is a single leaf)
+    uint32_t depth = 0;
+};
+
+// The bounds side of BVHBaseBuilder::recurse on a given topology: leaves accumulate their objects' time keys
+// (acc_bounds), inner nodes merge their children's (merge_slices_append), both collapse under the 1.4x union rule —
+// so everything downstream (bvh4_emit, traversal) sees the same kind of tree as from the SAH builder.
+class TopologyBoundsBuilder {
+  public:
+    TopologyBoundsBuilder(const uint32_t* ids, size_t n, ObjBoundsView ob, size_t per_leaf, const Bvh2Topology& t)
+        : ids_(ids), n_(n), ob_(ob), per_leaf_(per_leaf), t_(t) {
+        unsigned hw = std::thread::hardware_concurrency();
+        threads_left_ = (int)(hw > 1 ? hw - 1 : 0);
+    }
+    BaseNode* build() {
+        chunks_.emplace_back(new BaseChunk());
+        return node(t_.root, chunks_.back().get(), n_);
+    }
+
+  private:
+    void acc_bounds(size_t begin, size_t end, std::vector<BBox>& cache) const {
+        size_t max_len = 0;
+        for (size_t i = begin; i < end; ++i) max_len = std::max(max_len, ob_.count(ids_[i]));
+        cache.assign(max_len, BBox());
+        for (size_t i = begin; i < end; ++i) {
+            const BBox* b = ob_.ptr(ids_[i]);
+            size_t nb = ob_.count(ids_[i]);
+            if (nb == max_len) {
+                for (size_t k = 0; k < nb; ++k) cache[k] = bb_union(cache[k], b[k]);
+            } else {
+                float s = (float)(max_len - 1);
+                for (size_t k = 0; k < max_len; ++k) cache[k] = bb_union(cache[k], lerp_slice(b, nb, (float)k / s));
+            }
+        }
+    }
+    static void push_collapsed(const std::vector<BBox>& keys, std::vector<BBox>& out) {
+        BBox u;
+        for (auto& b : keys) u = bb_union(u, b);
+        float area = 0.0f;
+        for (auto& b : keys) area = area + bb_area(b);
+        float average_area = area / (float)keys.size();
+        if (bb_area(u) <= (average_area * USE_UNION_FACTOR))
+            out.push_back(u);
+        else
+            out.insert(out.end(), keys.begin(), keys.end());
+    }
+    // `weight`: an upper bound of the leaves below (only used to decide where to fork a thread)
+    BaseNode* node(int32_t ref, BaseChunk* chunk, size_t weight) {
+        chunk->nodes.emplace_back();
+        BaseNode* me = &chunk->nodes.back();
+        me->bounds_store = &chunk->bounds;
+        if (ref < 0) {
+            const uint32_t code = (uint32_t)(~ref);
+            const size_t begin = code >> 2, end = begin + (code & 3u);
+            if ((code & 3u) == 0u || (code & 3u) > per_leaf_ || end > n_) throw std::runtime_error("bad leaf in external BVH topology");
+            std::vector<BBox> cache;
+            acc_bounds(begin, end, cache);
+            me->b0 = (uint32_t)chunk->bounds.size();
+            push_collapsed(cache, chunk->bounds);
+            me->b1 = (uint32_t)chunk->bounds.size();
+            me->leaf = true;
+            me->obj_begin = (uint32_t)begin;
+            me->obj_end = (uint32_t)end;
+            return me;
+        }
+        if ((uint32_t)ref >= t_.n_internal) throw std::runtime_error("bad node in external BVH topology");
+        me->split_axis = t_.axis[ref];
+        BaseNode *c0 = nullptr, *c1 = nullptr;
+        bool spawned = false;
+        if (weight >= 32768) {
+            int left = threads_left_.fetch_sub(1);
+            if (left > 0) {
+                spawned = true;
+                BaseChunk* nc;
+                {
+                    std::lock_guard<std::mutex> g(mu_);
+                    chunks_.emplace_back(new BaseChunk());
+                    nc = chunks_.back().get();
+                }
+                std::thread th([&]() { c0 = node(t_.left[ref], nc, weight / 2); });
+                c1 = node(t_.right[ref], chunk, weight / 2);
+                th.join();
+                threads_left_.fetch_add(1);
+            } else {
+                threads_left_.fetch_add(1);
+            }
+        }
+        if (!spawned) {
+            c0 = node(t_.left[ref], chunk, weight / 2);
+            c1 = node(t_.right[ref], chunk, weight / 2);
+        }
+        me->c[0] = c0;
+        me->c[1] = c1;
+        std::vector<BBox> merged;
+        merge_slices_append(c0->bounds(), c0->nbounds(), c1->bounds(), c1->nbounds(), merged,
+                            [](const BBox& a, const BBox& b) { return bb_union(a, b); });
+        me->b0 = (uint32_t)chunk->bounds.size();
+        push_collapsed(merged, chunk->bounds);
+        me->b1 = (uint32_t)chunk->bounds.size();
+        return me;
+    }
+
+    const uint32_t* ids_;
+    size_t n_;
+    ObjBoundsView ob_;
+    size_t per_leaf_;
+    Bvh2Topology t_;
+    std::vector<std::unique_ptr<BaseChunk>> chunks_;
+    std::mutex mu_;
+    std::atomic<int> threads_left_{0};
+};
+
 // Flattened BVH4 with node indices local to this tree.
 struct Bvh4Flat {
     uint32_t root = PSY_NONE;  // child reference
@@ -362,16 +505,13 @@ inline PsyBBox4 bbox4_from(const BBox b[4]) {
     return o;
 }
 
-// construct_from_base (bvh4.rs:186-358).  `obj_base` is added to leaf object starts so that leaves
-// address the global triangle / instance arrays.
-inline uint32_t bvh4_emit(const BaseNode* node, uint32_t obj_base, Bvh4Flat& out) {
-    if (node->leaf) {
-        return PSY_CHILD_LEAF(obj_base + node->obj_begin, node->obj_end - node->obj_begin);
-    }
+// One BVH4 node of construct_from_base (bvh4.rs:186-358): picks the 2-4 children of binary node `node` (its
+// children, or their children where those are internal), the traversal code and the time-sampled child bounds, and
+// appends the node with its child references still unset.  Returns its index.
+inline uint32_t bvh4_make_node(const BaseNode* node, const BaseNode* children[4], int& child_count, Bvh4Flat& out) {
     const BaseNode* cl = node->c[0];
     const BaseNode* cr = node->c[1];
-    const BaseNode* children[4] = {nullptr, nullptr, nullptr, nullptr};
-    int child_count;
+    children[0] = children[1] = children[2] = children[3] = nullptr;
     uint8_t code;
     if (!cl->leaf) {
         if (!cr->leaf) {
@@ -407,7 +547,6 @@ inline uint32_t bvh4_emit(const BaseNode* node, uint32_t obj_base, Bvh4Flat& out
         if (children[i]) bounds_len = std::max(bounds_len, children[i]->nbounds());
 
     uint32_t my_index = (uint32_t)out.nodes.size();
-    out.nodes.emplace_back();
     PsyBvh4Node nd{};
     nd.traversal_code = code;
     nd.n_children = (uint32_t)child_count;
@@ -431,19 +570,128 @@ inline uint32_t bvh4_emit(const BaseNode* node, uint32_t obj_base, Bvh4Flat& out
         }
     }
     for (int i = 0; i < 4; ++i) nd.child[i] = PSY_NONE;
-    for (int i = 0; i < child_count; ++i) nd.child[i] = bvh4_emit(children[i], obj_base, out);
-    out.nodes[my_index] = nd;
+    out.nodes.push_back(nd);
     return my_index;
+}
+
+// construct_from_base (bvh4.rs:186-358).  `obj_base` is added to leaf object starts so that leaves
+// address the global triangle / instance arrays.
+inline uint32_t bvh4_emit(const BaseNode* node, uint32_t obj_base, Bvh4Flat& out) {
+    if (node->leaf) return PSY_CHILD_LEAF(obj_base + node->obj_begin, node->obj_end - node->obj_begin);
+    const BaseNode* children[4];
+    int child_count = 0;
+    const uint32_t my_index = bvh4_make_node(node, children, child_count, out);
+    for (int i = 0; i < child_count; ++i) {
+        const uint32_t c = bvh4_emit(children[i], obj_base, out);
+        out.nodes[my_index].child[i] = c;
+    }
+    return my_index;
+}
+
+// construct_from_base on the host's cores: the BVH4 nodes of the first levels are emitted here, every subtree below
+// them by its own task into its own Bvh4Flat, and the pieces are then appended (child references and key bases
+// shifted).  Node NUMBERING differs from the serial emit (subtrees are contiguous either way); nothing reads it.
+struct Bvh4Task {
+    const BaseNode* node;
+    uint32_t parent;  // node index in the top part
+    int slot;         // child slot to patch
+};
+inline uint32_t bvh4_emit_top(const BaseNode* node, uint32_t obj_base, Bvh4Flat& out, int depth, int cut,
+                              std::vector<Bvh4Task>& tasks, uint32_t parent, int slot) {
+    if (node->leaf) return PSY_CHILD_LEAF(obj_base + node->obj_begin, node->obj_end - node->obj_begin);
+    if (depth == cut) {
+        tasks.push_back(Bvh4Task{node, parent, slot});
+        return PSY_NONE;  // patched once the subtree is built
+    }
+    const BaseNode* children[4];
+    int child_count = 0;
+    const uint32_t my_index = bvh4_make_node(node, children, child_count, out);
+    for (int i = 0; i < child_count; ++i) {
+        const uint32_t c = bvh4_emit_top(children[i], obj_base, out, depth + 1, cut, tasks, my_index, i);
+        out.nodes[my_index].child[i] = c;
+    }
+    return my_index;
+}
+inline uint32_t bvh4_emit_parallel(const BaseNode* root, uint32_t obj_base, Bvh4Flat& out) {
+    std::vector<Bvh4Task> tasks;
+    uint32_t r = bvh4_emit_top(root, obj_base, out, 0, 3, tasks, PSY_NONE, 0);
+    if (tasks.empty()) return r;
+    std::vector<Bvh4Flat> parts(tasks.size());
+    std::vector<uint32_t> roots(tasks.size());
+    std::atomic<size_t> next{0};
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = std::min<size_t>(hw ? hw : 1, tasks.size());
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; ++t)
+        th.emplace_back([&]() {
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= tasks.size()) break;
+                roots[i] = bvh4_emit(tasks[i].node, obj_base, parts[i]);
+            }
+        });
+    for (auto& x : th) x.join();
+    // append the parts: sizes first, then copy in parallel
+    std::vector<size_t> node_off(tasks.size()), key_off(tasks.size());
+    size_t n_nodes = out.nodes.size(), n_keys = out.motion.size();
+    for (size_t i = 0; i < tasks.size(); ++i) {
+        node_off[i] = n_nodes, key_off[i] = n_keys;
+        n_nodes += parts[i].nodes.size(), n_keys += parts[i].motion.size();
+    }
+    out.nodes.resize(n_nodes);
+    out.motion.resize(n_keys);
+    parallel_for(tasks.size(), 1, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) {
+            const uint32_t no = (uint32_t)node_off[i], ko = (uint32_t)key_off[i];
+            for (size_t j = 0; j < parts[i].nodes.size(); ++j) {
+                PsyBvh4Node nd = parts[i].nodes[j];
+                for (int c = 0; c < 4; ++c)
+                    if (nd.child[c] != PSY_NONE && !PSY_CHILD_IS_LEAF(nd.child[c])) nd.child[c] += no;
+                if (nd.n_keys > 1) nd.key_base += ko;
+                out.nodes[no + j] = nd;
+            }
+            std::copy(parts[i].motion.begin(), parts[i].motion.end(), out.motion.begin() + ko);
+        }
+    });
+    for (size_t i = 0; i < tasks.size(); ++i) out.nodes[tasks[i].parent].child[tasks[i].slot] = roots[i] + (uint32_t)node_off[i];
+    return r;
 }
 
 // BVH4::from_objects (bvh4.rs:58-95): reorders ids in place.
 inline Bvh4Flat build_bvh4(uint32_t* ids, size_t n, ObjBoundsView ob, size_t objects_per_leaf, uint32_t obj_base) {
     Bvh4Flat out;
     if (n == 0) return out;
+    const bool timing = getenv("PSY_BUILD_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
     BVHBaseBuilder b(ids, n, ob, objects_per_leaf);
     BaseNode* root = b.build();
-    out.root = bvh4_emit(root, obj_base, out);
+    auto t1 = std::chrono::steady_clock::now();
+    out.root = n >= 65536 ? bvh4_emit_parallel(root, obj_base, out) : bvh4_emit(root, obj_base, out);
+    if (timing && n > 100000)
+        std::fprintf(stderr, "[build] %zu objects: binary tree %.3fs, BVH4 collapse %.3fs\n", n,
+                     std::chrono::duration<double>(t1 - t0).count(),
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
     out.depth = (uint32_t)(b.depth() / 2 + 1);
+    out.bounds.assign(root->bounds(), root->bounds() + root->nbounds());
+    return out;
+}
+
+// The same BVH4 from an externally built topology over the ordered id list (GPU LBVH).
+inline Bvh4Flat build_bvh4_from_topology(const uint32_t* ids, size_t n, ObjBoundsView ob, size_t objects_per_leaf,
+                                         uint32_t obj_base, const Bvh2Topology& topo) {
+    Bvh4Flat out;
+    if (n == 0) return out;
+    const bool timing = getenv("PSY_BUILD_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    TopologyBoundsBuilder b(ids, n, ob, objects_per_leaf, topo);
+    BaseNode* root = b.build();
+    auto t1 = std::chrono::steady_clock::now();
+    out.root = n >= 65536 ? bvh4_emit_parallel(root, obj_base, out) : bvh4_emit(root, obj_base, out);
+    if (timing && n > 100000)
+        std::fprintf(stderr, "[build] %zu objects: bounds on the external topology %.3fs, BVH4 collapse %.3fs\n", n,
+                     std::chrono::duration<double>(t1 - t0).count(),
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
+    out.depth = (uint32_t)(topo.depth / 2 + 1);
     out.bounds.assign(root->bounds(), root->bounds() + root->nbounds());
     return out;
 }

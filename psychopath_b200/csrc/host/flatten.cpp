@@ -17,6 +17,27 @@
 
 namespace psyh {
 
+namespace {
+std::mutex g_topo_mu;
+MeshTopologyFn g_topo_fn = nullptr;
+void* g_topo_ctx = nullptr;
+uint32_t g_topo_min_tris = 0;
+double g_topo_seconds = 0.0;
+uint32_t g_topo_meshes = 0;
+}  // namespace
+
+void set_mesh_topology_builder(MeshTopologyFn fn, void* ctx, uint32_t min_tris) {
+    std::lock_guard<std::mutex> g(g_topo_mu);
+    g_topo_fn = fn, g_topo_ctx = ctx, g_topo_min_tris = min_tris;
+}
+double take_mesh_topology_seconds(uint32_t* meshes_built) {
+    std::lock_guard<std::mutex> g(g_topo_mu);
+    double s = g_topo_seconds;
+    if (meshes_built) *meshes_built = g_topo_meshes;
+    g_topo_seconds = 0.0, g_topo_meshes = 0;
+    return s;
+}
+
 PsyColor color_from_rec709(float r, float g, float b) {
     PsyColor c;
     c.kind = PSY_COLOR_XYZ;
@@ -115,14 +136,18 @@ struct Flattener {
     void append_bvh(const Bvh4Flat& bvh, uint32_t& root_out) {
         uint32_t node_base = (uint32_t)fs.nodes.size();
         uint32_t key_base = (uint32_t)fs.motion_bounds.size();
-        for (PsyBvh4Node nd : bvh.nodes) {
-            for (int i = 0; i < 4; ++i) {
-                uint32_t c = nd.child[i];
-                if (c != PSY_NONE && !PSY_CHILD_IS_LEAF(c)) nd.child[i] = c + node_base;
+        fs.nodes.resize((size_t)node_base + bvh.nodes.size());
+        parallel_for(bvh.nodes.size(), 65536, [&](size_t b0, size_t e0) {
+            for (size_t j = b0; j < e0; ++j) {
+                PsyBvh4Node nd = bvh.nodes[j];
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t c = nd.child[i];
+                    if (c != PSY_NONE && !PSY_CHILD_IS_LEAF(c)) nd.child[i] = c + node_base;
+                }
+                if (nd.n_keys > 1) nd.key_base += key_base;
+                fs.nodes[(size_t)node_base + j] = nd;
             }
-            if (nd.n_keys > 1) nd.key_base += key_base;
-            fs.nodes.push_back(nd);
-        }
+        });
         fs.motion_bounds.insert(fs.motion_bounds.end(), bvh.motion.begin(), bvh.motion.end());
         uint32_t r = bvh.root;
         if (r != PSY_NONE && !PSY_CHILD_IS_LEAF(r)) r += node_base;
@@ -166,42 +191,89 @@ struct Flattener {
                     fs.normals[o++] = p.z;
                 }
         }
+        const bool timing = getenv("PSY_BUILD_TIMING") != nullptr && nt > 100000;
+        auto tm0 = std::chrono::steady_clock::now();
         // per-triangle bounds for every time sample (triangle_mesh.rs:86-99)
         std::vector<BBox> bounds(nt * k);
         std::vector<uint32_t> begin(nt + 1);
         for (size_t i = 0; i < nt; ++i) {
-            begin[i] = (uint32_t)(i * k);
             auto& t = m.tris[i];
             if (t[0] >= vc || t[1] >= vc || t[2] >= vc) throw std::runtime_error("triangle index out of range");
-            for (size_t ti = 0; ti < k; ++ti) {
-                V3 p0 = m.verts[ti][t[0]], p1 = m.verts[ti][t[1]], p2 = m.verts[ti][t[2]];
-                BBox b;
-                b.min = vmin(p0, vmin(p1, p2));
-                b.max = vmax(p0, vmax(p1, p2));
-                bounds[i * k + ti] = b;
-            }
         }
+        parallel_for(nt, 65536, [&](size_t b0, size_t e0) {
+            for (size_t i = b0; i < e0; ++i) {
+                begin[i] = (uint32_t)(i * k);
+                auto& t = m.tris[i];
+                for (size_t ti = 0; ti < k; ++ti) {
+                    V3 p0 = m.verts[ti][t[0]], p1 = m.verts[ti][t[1]], p2 = m.verts[ti][t[2]];
+                    BBox b;
+                    b.min = vmin(p0, vmin(p1, p2));
+                    b.max = vmax(p0, vmax(p1, p2));
+                    bounds[i * k + ti] = b;
+                }
+            }
+        });
         begin[nt] = (uint32_t)(nt * k);
+        if (timing)
+            std::fprintf(stderr, "[build] mesh %zu triangles x %zu keys: triangle bounds %.3fs\n", nt, k,
+                         std::chrono::duration<double>(std::chrono::steady_clock::now() - tm0).count());
         std::vector<uint32_t> ids(nt);
         std::iota(ids.begin(), ids.end(), 0u);
         pm.tri_base = (uint32_t)(fs.tris.size() / 4);
         pm.tri_count = (uint32_t)nt;
         if ((size_t)pm.tri_base + nt > PSY_MAX_LEAF_START) throw std::runtime_error("too many triangles");
-        Bvh4Flat bvh = build_bvh4(ids.data(), nt, ObjBoundsView{bounds.data(), begin.data()}, 3, pm.tri_base);
-        fs.tris.reserve(fs.tris.size() + nt * 4);
-        for (size_t i = 0; i < nt; ++i) {
-            auto& t = m.tris[ids[i]];
-            // (v0, v2, v1, original index) — triangle_mesh.rs:80
-            fs.tris.push_back(t[0]);
-            fs.tris.push_back(t[2]);
-            fs.tris.push_back(t[1]);
-            fs.tris.push_back(ids[i]);
+        Bvh4Flat bvh;
+        bool built = false;
+        {
+            // triangle order + binary topology from the registered external (GPU LBVH) builder
+            MeshTopologyFn fn;
+            void* fctx;
+            uint32_t fmin;
+            {
+                std::lock_guard<std::mutex> g(g_topo_mu);
+                fn = g_topo_fn, fctx = g_topo_ctx, fmin = g_topo_min_tris;
+            }
+            if (fn && nt >= fmin && nt > 3) {
+                std::vector<int32_t> left(nt - 1), right(nt - 1);
+                std::vector<uint8_t> axis(nt - 1);
+                Bvh2Topology topo;
+                auto t0 = std::chrono::steady_clock::now();
+                int32_t rc = fn(fctx, fs.verts.data() + (size_t)pm.vert_base * 3, (uint32_t)vc, (uint32_t)k, &m.tris[0][0],
+                                (uint32_t)nt, 3, ids.data(), left.data(), right.data(), axis.data(), &topo.n_internal, &topo.root,
+                                &topo.depth);
+                double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                if (rc == 0 && topo.depth <= BVH_MAX_DEPTH) {
+                    topo.left = left.data(), topo.right = right.data(), topo.axis = axis.data();
+                    bvh = build_bvh4_from_topology(ids.data(), nt, ObjBoundsView{bounds.data(), begin.data()}, 3, pm.tri_base,
+                                                   topo);
+                    built = true;
+                    std::lock_guard<std::mutex> g(g_topo_mu);
+                    g_topo_seconds += dt, g_topo_meshes += 1;
+                } else {
+                    std::iota(ids.begin(), ids.end(), 0u);  // fall back to the SAH builder on the original order
+                }
+            }
         }
+        if (!built) bvh = build_bvh4(ids.data(), nt, ObjBoundsView{bounds.data(), begin.data()}, 3, pm.tri_base);
+        auto tm1 = std::chrono::steady_clock::now();
+        const size_t tri_off = fs.tris.size();
+        fs.tris.resize(tri_off + nt * 4);
+        parallel_for(nt, 65536, [&](size_t b0, size_t e0) {
+            for (size_t i = b0; i < e0; ++i) {
+                auto& t = m.tris[ids[i]];
+                // (v0, v2, v1, original index) — triangle_mesh.rs:80
+                uint32_t* o = fs.tris.data() + tri_off + i * 4;
+                o[0] = t[0], o[1] = t[2], o[2] = t[1], o[3] = ids[i];
+            }
+        });
         append_bvh(bvh, pm.root);
         pm.bvh_depth = bvh.depth;
         pm.bounds_base = (uint32_t)fs.obj_bounds.size();
         pm.bounds_count = (uint32_t)bvh.bounds.size();
         for (auto& b : bvh.bounds) fs.obj_bounds.push_back(to_abi(b));
+        if (timing)
+            std::fprintf(stderr, "[build] triangle list + node append %.3fs\n",
+                         std::chrono::duration<double>(std::chrono::steady_clock::now() - tm1).count());
         uint32_t idx = (uint32_t)fs.meshes.size();
         fs.meshes.push_back(pm);
         mesh_cache[&m] = idx;

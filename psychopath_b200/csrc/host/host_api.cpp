@@ -85,6 +85,13 @@ int psyh_synth_instanced(uint32_t asset_quads, uint32_t n_assets, uint32_t n_clu
     });
 }
 
+// registers the builder of mesh BVH topologies (psy_build_mesh_topology of the CUDA library) for meshes
+// of at least `min_tris` triangles; fn == NULL restores the host SAH builder for everything.
+void psyh_set_mesh_topology_builder(void* fn, void* ctx, uint32_t min_tris) {
+    set_mesh_topology_builder(reinterpret_cast<MeshTopologyFn>(fn), ctx, min_tris);
+}
+double psyh_take_mesh_topology_seconds(uint32_t* meshes_built) { return take_mesh_topology_seconds(meshes_built); }
+
 const PsySceneDesc* psyh_scene_desc(void* scene) { return &static_cast<HostScene*>(scene)->flat->desc; }
 double psyh_build_seconds(void* scene) { return static_cast<HostScene*>(scene)->flat->build_seconds; }
 const char* psyh_output_path(void* scene) { return static_cast<HostScene*>(scene)->flat->output_path.c_str(); }

@@ -31,6 +31,7 @@ void psyh_scene_free(void* scene);
 int psyh_write_png(const char* path, const float* xyz, uint32_t w, uint32_t h);
 int psyh_write_exr(const char* path, const float* xyz, uint32_t w, uint32_t h);
 size_t psyh_bucket_base64(const float* xyz, uint32_t w, uint32_t h, char* out, size_t cap);
+void psyh_set_mesh_topology_builder(void* fn, void* ctx, uint32_t min_tris);
 }
 
 namespace {
@@ -82,7 +83,7 @@ int main(int argc, char** argv) {
     uint32_t spp = 0, spb = 0, crop[4] = {0, 0, 0, 0};
     int device = 0;
     std::vector<int> devices;  // --gpus N / --device-list a,b,c (flags the GPU host adds)
-    bool counters = false;
+    bool counters = false, gpu_build = false;
     std::string probe_in, probe_out;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -126,6 +127,8 @@ int main(int argc, char** argv) {
             if (devices.empty()) die("Argument '--device-list' needs a comma-separated list of CUDA device indices");
         } else if (a == "--counters") {
             counters = true;
+        } else if (a == "--gpu-build") {
+            gpu_build = true;  // mesh BVH order + topology from the GPU LBVH build
         } else if (a == "--probe-rays") {
             need(1);
             probe_in = argv[++i];
@@ -183,6 +186,7 @@ int main(int argc, char** argv) {
     PsyContext* ctx = nullptr;
     if (devices.empty()) devices.push_back(device);
     if (psy_init(devices.data(), (int)devices.size(), &ctx) != PSY_OK) die(std::string("psy_init: ") + psy_last_error());
+    if (gpu_build) psyh_set_mesh_topology_builder(reinterpret_cast<void*>(&psy_build_mesh_topology), ctx, 1u << 16);
     std::string device_names;
     for (size_t k = 0; k < devices.size(); ++k) device_names += (k ? "," : "") + std::to_string(devices[k]);
 
