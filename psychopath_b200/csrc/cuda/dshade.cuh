@@ -629,6 +629,17 @@ PSY_DEV void closure_sample(const Closure& cl, const ShadeCtx& sc, V3 inc, float
 // only feed the two partially-occluded cases, so they are evaluated there (pure functions: same bits).
 PSY_NOINLINE float sphere_lambert(float nlcos, float rcos) {
     float rsin2 = 1.0f - (rcos * rcos);
+    // The two acos calls below only pick the case.  acos is monotone, so `nl < pi/2 - r` is the same as
+    // `nlcos > sin(r)`, and sin(r) = sqrt(1 - rcos^2) exactly.  With an upper bound of sin(r) that covers the
+    // rounding of rsin2 (<= 6e-8 absolute: one rounded product, the subtraction is exact) and a margin far above
+    // what rounding in acosf (<= 2 ulp) and in `H_PI - r` can move the comparison (2e-6 against < 5e-7), the outer
+    // two cases are decided without the calls — same branch, same arithmetic in it, same bits.  The light-tree walk
+    // calls this 8 times per level and most children are small and far away: the first case.
+    {
+        const float rsin_hi = sqrtf(rsin2 + 2.0e-7f) + 2.0e-6f;
+        if (nlcos > rsin_hi) return nlcos * rsin2;
+        if (nlcos < -rsin_hi) return 0.0f;
+    }
     float nl = PSY_ACOSF(nlcos);
     float r = PSY_ACOSF(rcos);
     if (nl < (PSY_H_PI - r)) return nlcos * rsin2;

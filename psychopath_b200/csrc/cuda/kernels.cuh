@@ -599,8 +599,11 @@ __global__ void __launch_bounds__(PSY_LIGHT_THREADS) k_shade_light(DScene S, Pat
 // its own kernel so that this loop-heavy, small piece of code is not evicted from the instruction cache by
 // the f64 light-sampling and spectral code of k_shade (k_shade<LAMBERT> was stalled on instruction fetch
 // for 12 of 17 cycles per issue when it contained both, profiles/r1_shade_lambert_r1g.txt).
+// 8 blocks per SM (64 registers): the walk is a chain of dependent arithmetic per child (normalize, acos / asin,
+// divisions) and the kernel ran at 40 % of the issue slots with 14 warps per SM; 32 warps hide it better than the
+// few spilled registers cost (shade stage 253 -> 229 ms per C5 frame at 16 spp; 6 / 10 / 12 blocks: 237 / 229 / 233).
 template <int CLS>
-__global__ void __launch_bounds__(128) k_shade_select(DScene S, PathPool P, Bucket b, ShadeQueues Q) {
+__global__ void __launch_bounds__(128, 8) k_shade_select(DScene S, PathPool P, Bucket b, ShadeQueues Q) {
     constexpr uint32_t KIND = CLS == SHADE_LAMBERT ? (uint32_t)PSY_SHADER_LAMBERT : (uint32_t)PSY_SHADER_GGX;
     const uint32_t n = Q.count[CLS];
     const uint32_t* __restrict__ queue = Q.q[CLS];
