@@ -15,7 +15,8 @@ total work is fixed, so scaling is "strong".
             description (H2D) and fetches the finished image (D2H)
   roofline  k_trace_pool (the dominant kernel): algorithmic bytes of SURVEY.md 8(d)'s formula, with visit
             counts measured by the counting trace kernel, over the CUDA-event time of the trace launches;
-            traffic = the kernel's measured DRAM bytes per ray (profiles/r1_trace_dram.json) x rays per launch
+            traffic = the kernel's measured DRAM bytes per ray (profiles/r2_trace_dram.json, keyed to the kernel
+            sources' hash) x rays per launch
   cpu_baseline / --impl reference: the CPU oracle (restated reference path; the Rust reference cannot be
             built here) on the host cores, on a bounded sample of the same workload.
 """
@@ -134,8 +135,28 @@ def algorithmic_bytes_per_ray(st, keys_node=1.0, keys_vert=1, keys_xform=1):
                "instances_per_ray": n_inst}
 
 
+def native_oracle():
+    """the CPU baseline is timed with `-march=native`.  The oracle library that travels with the repo is
+    built for x86-64-v3 (it must run on whatever box the tests land on); for timing, it is rebuilt here, on the box
+    that runs the bench, for that box's own CPU (same sources, same -ffp-contract=off; ~6 s)."""
+    if os.environ.get("PSY_ORACLE_LIB"):
+        return os.environ["PSY_ORACLE_LIB"]
+    odir = os.path.join(REPO, "oracle")
+    out = os.path.join(odir, "_native", "liboracle.so")
+    try:
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O3", "-march=native", "-ffp-contract=off", "-fno-fast-math", "-fPIC",
+                               "-pthread", "-shared", "-o", out, os.path.join(odir, "oracle.cpp")],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
+        os.environ["PSY_ORACLE_LIB"] = out
+        return out
+    except Exception:
+        return None
+
+
 def cpu_sample(scene, spp, seed, target_s=15.0, threads=0):
     """Times the oracle on a bounded number of Hilbert-ordered buckets of the same workload."""
+    native_oracle()
     import oracle_lib as O
     # Buckets are drawn evenly from the whole Hilbert list (oracle_render_image), so the rate of a small
     # probe extrapolates; grow the sample until it takes about target_s (at most 3 rounds, bounded).
@@ -205,6 +226,7 @@ def run_reference(args):
             "config": {"workload": WORKLOAD_DESC[name], "timing": "bounded CPU sample per step"},
             "msamples_s": sum(x["msamples_s"] for x in vals) / len(vals),
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": last["threads"], "kind": "port", "sample": sample,
+                             "build": "-O3 -march=native" if os.environ.get("PSY_ORACLE_LIB") else "-O3 -march=x86-64-v3",
                              "note": "restated reference CPU path (oracle/); the Rust reference cannot be built here"},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "host_build_s": build_s}
@@ -398,13 +420,21 @@ def main():
         achieved = (my_rays * b_ray) / max(float(t[3]) * 1e-3, 1e-12) / 1e9
         # DRAM bytes of the trace kernel per launch: bytes per ray from the committed ncu capture of the same
         # scene (profiles/r1_trace_dram.json) x the rays one launch of this run traces on average
+        # (ncu cannot run inside this process: the capture is keyed to a hash of the kernel's sources and is reported
+        # only while it still describes the kernel that ran; tools/trace_traffic.py refreshes it)
         traffic, traffic_note = None, None
-        tp = os.path.join(REPO, "profiles", "r1_trace_dram.json")
+        tp = os.path.join(REPO, "profiles", "r2_trace_dram.json")
         if os.path.exists(tp) and name == "C5":
+            sys.path.insert(0, os.path.join(REPO, "tools"))
+            from trace_traffic import kernel_source_hash
             td = json.load(open(tp))
-            traffic = td["dram_bytes_per_ray"] * my_rays / max(float(t[4]), 1.0)
-            traffic_note = "ncu dram__bytes_read+write per ray (%.0f B, profiles/r1_trace_dram.json) x rays per launch; " \
-                           "algorithmic bytes per launch: %.3g" % (td["dram_bytes_per_ray"], b_ray * my_rays / max(float(t[4]), 1.0))
+            if td.get("kernel_source_sha256") == kernel_source_hash():
+                traffic = td["dram_bytes_per_ray"] * my_rays / max(float(t[4]), 1.0)
+                traffic_note = "ncu dram__bytes_read+write per ray (%.0f B, profiles/r2_trace_dram.json, same kernel sources) x " \
+                               "rays per launch; algorithmic bytes per launch: %.3g" % (
+                                   td["dram_bytes_per_ray"], b_ray * my_rays / max(float(t[4]), 1.0))
+            else:
+                traffic_note = "profiles/r2_trace_dram.json was captured for other kernel sources: not reported" 
         roofline = {"bound": "hbm", "kernel": "k_trace_pool", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "traffic_note": traffic_note,
                     "peak_kind": pk_kind,
@@ -416,6 +446,7 @@ def main():
         if not args.no_cpu_baseline:
             c = cpu_sample(scene, spp, seed, target_s=15.0)
             cpu = {"value": c["mrays_s"], "unit": "Mrays/s", "cores": c["threads"], "kind": "port",
+                   "build": "-O3 -march=native" if os.environ.get("PSY_ORACLE_LIB") else "-O3 -march=x86-64-v3",
                    "msamples_s": c["msamples_s"], "seconds": c["seconds"],
                    "sample": f"{c['buckets']} Hilbert-ordered 4x4-pixel buckets x {spp} spp of the same scene "
                              f"({c['samples']} samples, {c['rays']} rays)"}

@@ -35,9 +35,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(ORACLE_LIB):
+    path = os.environ.get("PSY_ORACLE_LIB", ORACLE_LIB)  # bench.py: the -march=native build made on the box
+    if not os.path.exists(path):
         build_oracle()
-    lib = C.CDLL(ORACLE_LIB)
+        path = ORACLE_LIB
+    lib = C.CDLL(path)
     u32, f32 = C.c_uint32, C.c_float
     D = C.POINTER(abi.PsySceneDesc)
     lib.oracle_trace_rays.argtypes = [D, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
