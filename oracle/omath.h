@@ -23,18 +23,20 @@ namespace orc {
 // The eight libm functions of the path.  Default: glibc, as the reference (Rust std) uses.  Strict mode
 // (oracle_set_strict_math): the deterministic functions of include/psy_detmath.h, which the strict build of the
 // CUDA path uses as well — then CPU and GPU compute every sample with the same bits.
-inline bool& strict_math() {
-    static bool on = false;
-    return on;
-}
-inline float m_sinf(float x) { return strict_math() ? psy_det_sinf(x) : std::sin(x); }
-inline float m_cosf(float x) { return strict_math() ? psy_det_cosf(x) : std::cos(x); }
-inline float m_acosf(float x) { return strict_math() ? psy_det_acosf(x) : std::acos(x); }
-inline float m_asinf(float x) { return strict_math() ? psy_det_asinf(x) : std::asin(x); }
-inline double m_sin(double x) { return strict_math() ? psy_det_sin(x) : std::sin(x); }
-inline double m_cos(double x) { return strict_math() ? psy_det_cos(x) : std::cos(x); }
-inline double m_acos(double x) { return strict_math() ? psy_det_acos(x) : std::acos(x); }
-inline double m_log(double x) { return strict_math() ? psy_det_log(x) : std::log(x); }
+// (plain globals, tested with an unlikely hint: the default path must cost what calling libm costs — this code is
+// also the timed CPU baseline)
+inline bool g_strict_math = false;
+inline bool g_debug_trace = false;  // oracle_set_debug: per-sample trace of one path
+#define ORC_UNLIKELY(x) __builtin_expect(!!(x), 0)
+inline bool& strict_math() { return g_strict_math; }
+inline float m_sinf(float x) { return ORC_UNLIKELY(g_strict_math) ? psy_det_sinf(x) : std::sin(x); }
+inline float m_cosf(float x) { return ORC_UNLIKELY(g_strict_math) ? psy_det_cosf(x) : std::cos(x); }
+inline float m_acosf(float x) { return ORC_UNLIKELY(g_strict_math) ? psy_det_acosf(x) : std::acos(x); }
+inline float m_asinf(float x) { return ORC_UNLIKELY(g_strict_math) ? psy_det_asinf(x) : std::asin(x); }
+inline double m_sin(double x) { return ORC_UNLIKELY(g_strict_math) ? psy_det_sin(x) : std::sin(x); }
+inline double m_cos(double x) { return ORC_UNLIKELY(g_strict_math) ? psy_det_cos(x) : std::cos(x); }
+inline double m_acos(double x) { return ORC_UNLIKELY(g_strict_math) ? psy_det_acos(x) : std::acos(x); }
+inline double m_log(double x) { return ORC_UNLIKELY(g_strict_math) ? psy_det_log(x) : std::log(x); }
 
 struct V3 {
     float x, y, z;

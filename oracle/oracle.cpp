@@ -718,7 +718,7 @@ struct LightSampler {
             float r2 = length2(bmax - bmin) * 0.25f;
             float inv_surface_area = 1.0f / r2;
             float approx_contrib = closure_estimate_sphere(sc, inc, dd, r2, nor, nor_g);
-            if (g_dbg_on)
+            if (ORC_UNLIKELY(g_dbg_on))
                 std::fprintf(stderr, "[oracle dbg]     child energy %.9g r2 %.9g dd (%.9g %.9g %.9g) contrib %.9g\n", (double)nd.energy,
                              (double)r2, (double)dd.x, (double)dd.y, (double)dd.z, (double)approx_contrib);
             return nd.energy * inv_surface_area * approx_contrib;
@@ -1009,7 +1009,7 @@ static Ray camera_ray(const PsySceneDesc& d, float x, float y, float time, float
 static uint32_t g_dbg_px = 0xFFFFFFFFu, g_dbg_py = 0, g_dbg_si = 0;
 #define ORC_DBG(...)                                                               \
     do {                                                                           \
-        if (px == g_dbg_px && py == g_dbg_py && sample_number == g_dbg_si) {       \
+        if (ORC_UNLIKELY(g_debug_trace) && px == g_dbg_px && py == g_dbg_py && sample_number == g_dbg_si) { \
             std::fprintf(stderr, "[oracle dbg] " __VA_ARGS__);                     \
             std::fprintf(stderr, "\n");                                            \
         }                                                                          \
@@ -1068,11 +1068,15 @@ struct LightPath {
                 next_lds_sequence();
                 float s4[4];
                 next_lds_samp(s4);
-                g_dbg_on = (px == g_dbg_px && py == g_dbg_py && sample_number == g_dbg_si);
-                sphere_lambert_debug() = g_dbg_on;
+                if (ORC_UNLIKELY(g_debug_trace)) {
+                    g_dbg_on = (px == g_dbg_px && py == g_dbg_py && sample_number == g_dbg_si);
+                    sphere_lambert_debug() = g_dbg_on;
+                }
                 LightSample li = ls.sample_scene(s4[0], s4[1], s4[2], s4[3], wavelength, time, isect);
-                g_dbg_on = false;
-                sphere_lambert_debug() = false;
+                if (ORC_UNLIKELY(g_debug_trace)) {
+                    g_dbg_on = false;
+                    sphere_lambert_debug() = false;
+                }
                 bool found_light = false;
                 ORC_DBG("  light kind %d pdf %.9g sel %.9g color (%.9g %.9g %.9g %.9g) pos (%.9g %.9g %.9g) nor (%.9g %.9g %.9g) dir (%.9g %.9g %.9g) s4 (%.9g %.9g %.9g)",
                         li.kind, (double)li.pdf, (double)li.selection_pdf, ORC_V4(li.color), ORC_V3(li.pos), ORC_V3(li.nor),
@@ -1490,7 +1494,10 @@ double oracle_det_f64(int fn, double x) {
 float oracle_det_f32(int fn, float x) {
     return fn == 0 ? psy_det_sinf(x) : fn == 1 ? psy_det_cosf(x) : fn == 2 ? psy_det_acosf(x) : psy_det_asinf(x);
 }
-void oracle_set_debug(uint32_t px, uint32_t py, uint32_t si) { g_dbg_px = px, g_dbg_py = py, g_dbg_si = si; }
+void oracle_set_debug(uint32_t px, uint32_t py, uint32_t si) {
+    g_dbg_px = px, g_dbg_py = py, g_dbg_si = si;
+    g_debug_trace = px != 0xFFFFFFFFu;
+}
 uint32_t oracle_hash_u32(uint32_t n, uint32_t seed) { return hash_u32(n, seed); }
 float oracle_golden_ratio_sample(uint32_t i, uint32_t scramble) { return golden_ratio_sample(i, scramble); }
 void oracle_get_sample_4d(uint32_t i, uint32_t ds, uint32_t px, uint32_t py, uint32_t seed, float* out) {

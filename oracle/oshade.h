@@ -311,10 +311,8 @@ inline void closure_sample(const Closure& cl, V3 inc, V3 nor, V3 nor_g, float u,
     }
 }
 
-inline bool& sphere_lambert_debug() {
-    static bool on = false;
-    return on;
-}
+inline bool g_sphere_lambert_debug = false;
+inline bool& sphere_lambert_debug() { return g_sphere_lambert_debug; }
 inline float sphere_lambert(float nlcos, float rcos) {
     float nlsin = std::sqrt(1.0f - (nlcos * nlcos));
     float rsin2 = 1.0f - (rcos * rcos);
@@ -326,7 +324,7 @@ inline float sphere_lambert(float nlcos, float rcos) {
     float h = nlcos * ((ycos * std::sqrt(rsin2 - ycos2)) + (rsin2 * m_asinf(ycos / rsin)));
     float nl = m_acosf(nlcos);
     float r = m_acosf(rcos);
-    if (sphere_lambert_debug())
+    if (ORC_UNLIKELY(g_sphere_lambert_debug))
         std::fprintf(stderr, "[oracle dbg]       sphere_lambert nlcos %.9g rcos %.9g nl %.9g r %.9g  nl-(H_PI-r) %.3g  ysin %.9g ycos2 %.3g g %.9g h %.9g\n",
                      (double)nlcos, (double)rcos, (double)nl, (double)r, (double)nl - ((double)H_PI - (double)r), (double)ysin,
                      (double)ycos2, (double)g, (double)h);
