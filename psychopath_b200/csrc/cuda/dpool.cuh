@@ -116,6 +116,36 @@ PSY_DEV LocalRay make_local_ray(const Xf& x, V3 orig, V3 dir) {
     return l;
 }
 
+// Rare code is kept OUT OF LINE: the kernel is ~48 KB of SASS and the warps of a scheduler are in different phases of
+// it, so every cold block inside a hot one costs instruction-cache misses (stall_no_instruction 1.2 cycles per issue;
+// moving the two blocks below out: trace -4 %).
+// The slab test of one node for rays with an infinite 1/direction component (bbox4.rs:63-97 with SSE's min / max).
+PSY_NOINLINE uint32_t slab4_sse(float4 bx0, float4 bx1, float4 by0, float4 by1, float4 bz0, float4 bz1, V3 ol, V3 di, float max_t,
+                                uint32_t n_children) {
+    const float ADJ = 1.00000024f;
+    uint32_t hits = 0;
+#define PSY_SLAB_S(LANE, BIT)                                                            \
+    {                                                                                    \
+        float t1x = (bx0.LANE - ol.x) * di.x;                                            \
+        float t1y = (by0.LANE - ol.y) * di.y;                                            \
+        float t1z = (bz0.LANE - ol.z) * di.z;                                            \
+        float t2x = (bx1.LANE - ol.x) * di.x;                                            \
+        float t2y = (by1.LANE - ol.y) * di.y;                                            \
+        float t2z = (bz1.LANE - ol.z) * di.z;                                            \
+        float fx = sse_max(t1x, t2x), fy = sse_max(t1y, t2y), fz = sse_max(t1z, t2z);    \
+        float nx = sse_min(t1x, t2x), ny = sse_min(t1y, t2y), nz = sse_min(t1z, t2z);    \
+        float far_t = sse_min(sse_min(fx, sse_min(fy, fz)) * ADJ, max_t);                \
+        float near_t = sse_max(sse_max(nx, ny), sse_max(nz, 0.0f));                      \
+        if (near_t < far_t) hits |= (1u << BIT);                                         \
+    }
+    PSY_SLAB_S(x, 0)
+    PSY_SLAB_S(y, 1)
+    if (n_children > 2u) PSY_SLAB_S(z, 2)
+    if (n_children > 3u) PSY_SLAB_S(w, 3)
+#undef PSY_SLAB_S
+    return hits;
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
     k_trace_pool(DScene S, PathPool P, const uint32_t* __restrict__ active, const uint32_t* __restrict__ count,
@@ -406,15 +436,8 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
 #undef SMIN
 #undef SMAX
                 } else {
-                    // axis-parallel rays can produce 0 * inf = NaN: keep the operand order of minps/maxps
-#define SMIN sse_min
-#define SMAX sse_max
-                    PSY_SLAB(x, 0)
-                    PSY_SLAB(y, 1)
-                    if (meta.w > 2u) PSY_SLAB(z, 2)
-                    if (meta.w > 3u) PSY_SLAB(w, 3)
-#undef SMIN
-#undef SMAX
+                    // axis-parallel rays can produce 0 * inf = NaN: keep the operand order of minps/maxps (rare: out of line)
+                    hits = slab4_sse(bx0, bx1, by0, by1, bz0, bz1, ol, di, max_t, meta.w);
                 }
 #undef PSY_SLAB
                 top = PSY_NONE;
@@ -621,7 +644,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                     pre.sx = __uint_as_float(rcb[3 * R + r]), pre.sy = __uint_as_float(rcb[4 * R + r]);
                     pre.sz = __uint_as_float(rcb[5 * R + r]);
                     const LightHit lh =
-                        light_instance_hit_inline(S.lights, S.light_shape, r1.x, kind, xform, orig, dir, ol, time, max_t, pre);
+                        light_instance_hit(S.lights, S.light_shape, r1.x, kind, xform, orig, dir, ol, time, max_t, pre);
                     if (COUNT) cnt.tri_tests += lh.tri_tests;
                     if (lh.kind != PSY_HIT_MISS) {
                         if (flags & RF_OCCL) {
