@@ -366,10 +366,15 @@ def main():
 
     # ---- end-to-end through the C ABI with host buffers: every step each rank uploads the scene description
     # (H2D), renders its tiles, the tiles are gathered, and rank 0 reads the finished image back (D2H) ----
+    # host buffers of the end-to-end arm are page-locked, as the timing contract asks: the scene arrays (registered once)
+    # and the image the result is read into (reused from step to step)
+    scene.pin()
+    e2e_img = torch.empty((ry, rx, 3), dtype=torch.float32, pin_memory=True).numpy() if rank == 0 else None
+
     def e2e_step():
         rr = api.Renderer(scene, device=local_rank)          # H2D: the whole scene description
         if world == 1:
-            img_, st_ = rr.render(max_samples_per_bucket=args.pool)   # D2H: the finished image
+            img_, st_ = rr.render(max_samples_per_bucket=args.pool, out=e2e_img)   # D2H: the finished image
         else:
             st_ = rr.render_shard(rank, world, max_samples_per_bucket=args.pool, work_queue_key=wq_key,
                                   buckets_per_gpu=args.buckets_per_gpu)
@@ -380,7 +385,7 @@ def main():
             t_ = torch.as_tensor(_W(), device=torch.device("cuda", local_rank))
             dist.reduce(t_, dst=0, op=dist.ReduceOp.SUM)
             torch.cuda.synchronize()
-            img_ = rr.fetch_image() if rank == 0 else None          # D2H on rank 0
+            img_ = rr.fetch_image(out=e2e_img) if rank == 0 else None          # D2H on rank 0
         rr.close()
         return img_, st_
     e2e_step()
@@ -453,7 +458,7 @@ def main():
 
     # ---- extra leg (rank 0, one GPU): BASELINE config 2, where EVERY node visit lerps two time keys ----
     c3 = None
-    if rank == 0 and name == "C5" and not args.no_c3 and not args.spp:
+    if rank == 0 and world == 1 and name == "C5" and not args.no_c3 and not args.spp:
         c3 = c3_leg(api, local_rank)
 
     if rank == 0:

@@ -393,6 +393,11 @@ int32_t psy_build_mesh_topology(PsyContext* ctx, const float* verts, uint32_t n_
                                 uint32_t n_tris, uint32_t tris_per_leaf, uint32_t* order, int32_t* left, int32_t* right,
                                 uint8_t* axis, uint32_t* n_internal, int32_t* root, uint32_t* depth);
 
+/* Page-locks / releases caller memory (cudaHostRegister): scene arrays that are uploaded every frame, result images
+ * that are fetched every frame.  Optional — every entry point also takes pageable memory, at a lower copy rate. */
+int32_t psy_host_register(void* ptr, size_t bytes);
+int32_t psy_host_unregister(void* ptr);
+
 /* The work counter behind work_queue_key, usable on its own by a host that schedules buckets itself (the reference's
  * Renderer::render, src/renderer.rs:138-180, with psy_render_bucket as the body of render_job): every process of the
  * node that opens the same key shares 64 counters, one per frame in flight; psy_work_queue_pull returns 0, 1, 2, ...

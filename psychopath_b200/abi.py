@@ -162,6 +162,7 @@ CUDA_SYMBOLS = [
     "psy_trace_rays", "psy_render_bucket", "psy_render_bucket_samples", "psy_render_image",
     "psy_render_image_shard", "psy_device_image", "psy_scene_stream", "psy_fetch_image", "psy_last_trace_timing",
     "psy_work_queue_open", "psy_work_queue_pull", "psy_work_queue_close", "psy_build_mesh_topology",
+    "psy_host_register", "psy_host_unregister",
 ]
 
 
@@ -220,6 +221,8 @@ def load_cuda(path=None):
     lib.psy_work_queue_open.argtypes = [u32, C.POINTER(C.c_void_p)]
     lib.psy_work_queue_pull.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.psy_work_queue_close.argtypes = [C.c_void_p]
+    lib.psy_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    lib.psy_host_unregister.argtypes = [C.c_void_p]
     for name in CUDA_SYMBOLS:
         if name not in ("psy_last_error", "psy_build_flags"):
             getattr(lib, name).restype = C.c_int32

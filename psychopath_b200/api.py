@@ -73,6 +73,7 @@ class Scene:
 
     def __del__(self):
         try:
+            self.unpin()
             if self._h:
                 host_lib().psyh_scene_free(self._h)
                 self._h = None
@@ -140,6 +141,27 @@ class Scene:
     def build_seconds(self):
         return host_lib().psyh_build_seconds(self._h)
 
+    def pin(self):
+        """Page-locks the large scene arrays (nodes, time-key bounds, triangles, vertices) so that every later upload
+        of this scene (Renderer(scene)) copies at the link's rate.  One-time cost; undone when the scene is freed."""
+        if getattr(self, "_pinned", None):
+            return
+        lib = cuda_lib()
+        d = self.desc.contents
+        regs = []
+        for ptr, nbytes in ((d.nodes, d.n_nodes * 128), (d.motion_bounds, d.n_motion_bounds * 96), (d.tris, d.n_tris * 16),
+                            (d.verts, d.n_vert_keys * 12), (d.normals, d.n_vert_keys * 12)):
+            addr = C.cast(ptr, C.c_void_p).value
+            if addr and nbytes >= (1 << 20):
+                if lib.psy_host_register(addr, nbytes) == 0:
+                    regs.append(addr)
+        self._pinned = regs
+
+    def unpin(self):
+        for addr in getattr(self, "_pinned", None) or []:
+            cuda_lib().psy_host_unregister(addr)
+        self._pinned = None
+
     def host_bytes(self):
         """Bytes of scene data the upload copies host->device."""
         d = self.desc.contents
@@ -190,6 +212,9 @@ class DeviceScene:
         if self._s:
             self.lib.psy_scene_destroy(self._s)
             self._s = C.c_void_p()
+        for img in getattr(self, "_pinned_images", []):
+            self.lib.psy_host_unregister(img.ctypes.data)
+        self._pinned_images = []
 
     def __del__(self):
         try:
@@ -253,7 +278,7 @@ class Renderer(Tracer):
 
     def render(self, max_samples_per_bucket=0, crop=None, thread_count=None, do_blender_output=False, spp=None,
                seed=None, counters=False, on_bucket=None, device_resident_only=False, strict_film=False,
-               buckets_per_gpu=0):
+               buckets_per_gpu=0, out=None):
         """Returns (image, stats): image is float32 (res_y, res_x, 3) XYZ, row 0 = top (None when
         device_resident_only).  thread_count is accepted for signature parity and ignored (the GPU is the
         worker pool).  do_blender_output=True streams every finished bucket to stdout in the reference's
@@ -262,7 +287,14 @@ class Renderer(Tracer):
         p = self._params(max_samples_per_bucket, crop, spp, seed, counters, device_resident_only, strict_film,
                          buckets_per_gpu)
         rx, ry = self.resolution
-        img = None if device_resident_only else np.zeros((ry, rx, 3), dtype=np.float32)
+        if device_resident_only:
+            img = None
+        elif out is not None:
+            # a caller-owned image, e.g. page-locked memory reused from frame to frame (pinned_image())
+            assert out.dtype == np.float32 and out.shape == (ry, rx, 3) and out.flags["C_CONTIGUOUS"]
+            img = out
+        else:
+            img = np.zeros((ry, rx, 3), dtype=np.float32)
         st = abi.PsyStats()
         cb = None
         if do_blender_output and on_bucket is None:
@@ -314,15 +346,23 @@ class Renderer(Tracer):
                     "psy_render_image_shard")
         return stats_dict(st)
 
+    def pinned_image(self):
+        """A page-locked (res_y, res_x, 3) float32 image to pass as render(out=...) / fetch_image(out=...)."""
+        rx, ry = self.resolution
+        img = np.zeros((ry, rx, 3), dtype=np.float32)
+        self._check(self.lib.psy_host_register(img.ctypes.data, img.nbytes), "psy_host_register")
+        self._pinned_images = getattr(self, "_pinned_images", []) + [img]
+        return img
+
     def device_image(self):
         ptr = C.c_void_p()
         n = C.c_size_t()
         self._check(self.lib.psy_device_image(self._s, C.byref(ptr), C.byref(n)), "psy_device_image")
         return ptr.value, n.value
 
-    def fetch_image(self):
+    def fetch_image(self, out=None):
         rx, ry = self.resolution
-        img = np.zeros((ry, rx, 3), dtype=np.float32)
+        img = out if out is not None else np.zeros((ry, rx, 3), dtype=np.float32)
         self._check(self.lib.psy_fetch_image(self._s, img.ctypes.data), "psy_fetch_image")
         return img
 

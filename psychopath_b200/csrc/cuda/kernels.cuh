@@ -246,14 +246,21 @@ PSY_DEV void probe_store(const DScene& S, const HitRec& h, const RayIn& ray, uin
 
 // Scene upload: the leaf-ordered triangle vertex array of one mesh, [v0 keys][v1 keys][v2 keys] per triangle
 // (the original triangle index rides in v0-key0 .w), from the mesh's vertex keys and (v0, v2, v1, orig) tuples.
+// The vertex indices are validated here as well (a bad one raises *bad_index and reads vertex 0): the host does not
+// walk the triangle list at upload.
 __global__ void __launch_bounds__(256) k_gather_tri_verts(const uint4* __restrict__ tris, const float* __restrict__ verts,
                                                           float4* __restrict__ out, uint32_t tri_base, uint32_t tri_count,
-                                                          uint32_t k, uint32_t vert_base, uint32_t tv_base) {
+                                                          uint32_t k, uint32_t vert_base, uint32_t vert_count,
+                                                          uint32_t tv_base, uint32_t* __restrict__ bad_index) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (uint64_t)tri_count * 3u * k) return;
     const uint32_t key = (uint32_t)(i % k), j = (uint32_t)((i / k) % 3u), t = (uint32_t)(i / (3u * (uint64_t)k));
     const uint4 idx = tris[tri_base + t];
-    const uint32_t vi = j == 0u ? idx.x : (j == 1u ? idx.y : idx.z);
+    uint32_t vi = j == 0u ? idx.x : (j == 1u ? idx.y : idx.z);
+    if (vi >= vert_count) {
+        *bad_index = 1u;
+        vi = 0u;
+    }
     const float* v = verts + ((size_t)vert_base + (size_t)vi * k + key) * 3u;
     const float w = (j == 0u && key == 0u) ? __uint_as_float(idx.w) : 0.0f;
     out[(size_t)tv_base + i] = make_float4(v[0], v[1], v[2], w);

@@ -889,6 +889,15 @@ static int32_t scene_create_one(PsyContext* ctx, const PsySceneDesc* s, PsyScene
     int32_t rc = PSY_OK;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    // PSY_UPLOAD_TIMING=1: where the time of an upload goes (stderr)
+    static const bool timing = getenv("PSY_UPLOAD_TIMING") != nullptr;
+    auto tp0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[upload] %-28s %.2f ms\n", what, std::chrono::duration<double>(now - tp0).count() * 1e3);
+        tp0 = now;
+    };
 
     // stack requirement
     {
@@ -950,6 +959,7 @@ static int32_t scene_create_one(PsyContext* ctx, const PsySceneDesc* s, PsyScene
         dpaths[i] = paths[i].d;
     }
 
+    lap("instance paths");
     // gather triangle vertices per leaf-ordered triangle: [v0 keys][v1 keys][v2 keys]
     std::vector<DMesh> dmeshes(s->n_meshes);
     size_t tv_total = 0;
@@ -969,11 +979,8 @@ static int32_t scene_create_one(PsyContext* ctx, const PsySceneDesc* s, PsyScene
             if ((uint64_t)pm.tri_base + pm.tri_count > s->n_tris) return fail(PSY_ERR_INVALID, "mesh triangle range");
             if (((uint64_t)pm.vert_base + (uint64_t)pm.vert_count * pm.n_keys) > s->n_vert_keys)
                 return fail(PSY_ERR_INVALID, "mesh vertex range");
-            for (uint32_t t = 0; t < pm.tri_count; ++t) {
-                const uint32_t* idx = s->tris + (size_t)(pm.tri_base + t) * 4;
-                if (idx[0] >= pm.vert_count || idx[1] >= pm.vert_count || idx[2] >= pm.vert_count)
-                    return fail(PSY_ERR_INVALID, "triangle vertex index out of range");
-            }
+            if (pm.tri_count && pm.vert_count == 0) return fail(PSY_ERR_INVALID, "mesh with triangles but no vertices");
+            // (the triangles' vertex indices are checked by the gather kernel on the device)
             o += (size_t)pm.tri_count * 3 * pm.n_keys;
         }
     }
@@ -1049,6 +1056,7 @@ static int32_t scene_create_one(PsyContext* ctx, const PsySceneDesc* s, PsyScene
                 }
     }
 
+    lap("index checks, path records");
     PsyScene* sc = new PsyScene();
     sc->ctx = ctx;
     sc->res_x = s->res_x, sc->res_y = s->res_y, sc->spp = s->spp, sc->seed = s->seed;
@@ -1091,10 +1099,17 @@ static int32_t scene_create_one(PsyContext* ctx, const PsySceneDesc* s, PsyScene
     UP(world_floats, s->world_floats, (size_t)s->n_world_floats);
     UP(meng, &MENG_SPECTRA[0][0], (size_t)186 * 95);
 #undef UP
+    lap("cudaMalloc + H2D enqueue");
     // Triangle vertices in leaf order, [v0 keys][v1 keys][v2 keys] per triangle, gathered on the device from the
     // vertex keys and the index tuples: the upload carries each vertex once instead of once per use.
-    DevBuf dverts;
+    DevBuf dverts, dbad;
     {
+        const uint32_t zero = 0;
+        cudaError_t e0_ = dbad.upload(&zero, 1, st);
+        if (e0_ != cudaSuccess) {
+            delete sc;
+            return fail(PSY_ERR_CUDA, std::string("upload: ") + cudaGetErrorString(e0_));
+        }
         cudaError_t e_ = sc->tri_verts.alloc(tv_total * sizeof(float4));
         if (e_ == cudaSuccess) e_ = dverts.upload(s->verts, (size_t)s->n_vert_keys * 3, st);
         if (e_ != cudaSuccess) {
@@ -1108,7 +1123,7 @@ static int32_t scene_create_one(PsyContext* ctx, const PsySceneDesc* s, PsyScene
             if (items == 0) continue;
             k_gather_tri_verts<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(
                 sc->tris.as<uint4>(), dverts.as<float>(), sc->tri_verts.as<float4>(), dm.tri_base, dm.tri_count, dm.n_keys,
-                dm.vert_base, dm.tv_base);
+                dm.vert_base, s->meshes[m].vert_count, dm.tv_base, dbad.as<uint32_t>());
         }
     }
     // the node blob, built on the device from the ABI arrays just uploaded
@@ -1130,12 +1145,19 @@ static int32_t scene_create_one(PsyContext* ctx, const PsySceneDesc* s, PsyScene
             return fail(PSY_ERR_CUDA, std::string("node blob build: ") + cudaGetErrorString(e_));
         }
     }
-    cudaError_t e = cudaStreamSynchronize(st);  // the staging vectors above die at return
+    uint32_t bad_index = 0;
+    cudaError_t e = cudaMemcpyAsync(&bad_index, dbad.p, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the staging vectors above die at return
     if (e != cudaSuccess) {
         delete sc;
         return fail(PSY_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
     }
+    if (bad_index) {
+        delete sc;
+        return fail(PSY_ERR_INVALID, "triangle vertex index out of range");
+    }
 
+    lap("vertex gather, node blob, sync");
     DScene& d = sc->d;
     d.nodes = sc->nodes.as<uint4>();
     d.nodes_tex = 0;
@@ -1220,6 +1242,7 @@ static int32_t scene_create_one(PsyContext* ctx, const PsySceneDesc* s, PsyScene
     d.meng_spectra = sc->meng.as<float>();
     d.res_x = s->res_x;
     d.res_y = s->res_y;
+    lap("texture object, DScene");
     *out = sc;
     return PSY_OK;
 }
@@ -1654,6 +1677,29 @@ int32_t psy_build_mesh_topology(PsyContext* ctx, const float* verts, uint32_t n_
     CK(cudaMemcpyAsync(order, dvals2.p, (size_t)n_tris * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    return PSY_OK;
+}
+
+// Page-locks caller memory (scene arrays, result images) so that the copies to and from the device run at the
+// link's rate instead of through the driver's staging buffers; a convenience over cudaHostRegister for hosts that
+// do not link the CUDA runtime themselves.
+int32_t psy_host_register(void* ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return PSY_OK;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return PSY_OK;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PSY_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+    }
+    return PSY_OK;
+}
+int32_t psy_host_unregister(void* ptr) {
+    if (!ptr) return PSY_OK;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) cudaGetLastError();
     return PSY_OK;
 }
 

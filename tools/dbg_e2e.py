@@ -1,20 +1,24 @@
-"""Debug helper: where the end-to-end overhead of one frame goes (scene upload, first render, image download, teardown)."""
-import os
-import sys
-import time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+"""Where the end-to-end overhead per frame goes: scene create (validate + H2D + device-side gathers), render, image
+fetch (D2H), destroy.  C5 scene at a small spp so that the fixed costs stand out."""
+import os, sys, time
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
 import bench
 from psychopath_b200 import api
-scene, _ = bench.build_scene("C5")
-scene.set_render(res=(3840, 2160), spp=int(sys.argv[1]) if len(sys.argv) > 1 else 4, seed=5)
-for it in range(3):
-    t0 = time.perf_counter()
-    r = api.Renderer(scene, device=0)
-    t1 = time.perf_counter()
-    img, st = r.render(max_samples_per_bucket=4 << 20)
-    t2 = time.perf_counter()
-    _, st2 = r.render(max_samples_per_bucket=4 << 20, device_resident_only=True)
-    t3 = time.perf_counter()
-    r.close()
-    t4 = time.perf_counter()
-    print(f"create {t1 - t0:.3f}s  first render+download {t2 - t1:.3f}s  resident render {t3 - t2:.3f}s  close {t4 - t3:.3f}s")
+kw = dict(bench.WORKLOADS["C5"]); kw["spp"] = 1
+scene = api.Scene.synth_instanced(**kw)
+r0 = api.Renderer(scene); r0.render(); r0.close()
+for i in range(4):
+    t0 = time.perf_counter(); r = api.Renderer(scene); t1 = time.perf_counter()
+    img, st = r.render(); t2 = time.perf_counter()
+    r.close(); t3 = time.perf_counter()
+    print(f"create {1e3*(t1-t0):.1f} ms  render+fetch {1e3*(t2-t1):.1f} ms (device {1e3*(st['trace_time']+st['ray_generation_time']+st['initial_ray_generation_time']+st['sample_writing_time']):.1f})  destroy {1e3*(t3-t2):.1f} ms")
+print("--- pinned scene arrays and pinned result image")
+scene.pin()
+r = api.Renderer(scene); out = r.pinned_image(); r.close()
+import numpy as np
+for i in range(4):
+    t0 = time.perf_counter(); r = api.Renderer(scene); t1 = time.perf_counter()
+    img, st = r.render(out=out); t2 = time.perf_counter()
+    r.close(); t3 = time.perf_counter()
+    print(f"create {1e3*(t1-t0):.1f} ms  render+fetch {1e3*(t2-t1):.1f} ms (device {1e3*(st['trace_time']+st['ray_generation_time']+st['initial_ray_generation_time']+st['sample_writing_time']):.1f})  destroy {1e3*(t3-t2):.1f} ms")
