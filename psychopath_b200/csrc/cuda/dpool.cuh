@@ -19,9 +19,11 @@
 // utilisation).  So the state is laid out to make the common steps ONE trip:
 //   * the top of the child-reference stack and a 4-entry ring window below it are in shared memory;
 //     pushes also write through to the global scratch area, which only deeper pops read back;
-//   * the ray is kept in the root assembly's, the current assembly's and the current mesh's space at
-//     once: leaving a mesh instance or a first-level assembly is detected by stack height and
-//     restores nothing from memory (deeper nesting saves / reloads through the scratch area);
+//   * the ray is kept in the current assembly's and the current mesh's space at once: leaving a mesh
+//     instance is detected by stack height and restores nothing from memory; leaving a first-level
+//     assembly is detected the same way and reloads the root-space ray, written once per ray to the
+//     scratch area (it used to sit in shared memory: 6 of 33 words, and with them the SM's L1 —
+//     trace -5 %); deeper nesting saves / reloads through the scratch area;
 //   * the triangle-vertex base of the current mesh is in the state, so a triangle step loads its
 //     vertices (and the mesh's local->world matrix from scratch) straight away;
 //   * node bounds are fetched together with the child words, before the motion-key test, and through
@@ -31,8 +33,11 @@
 
 namespace psyd {
 
+// Rays per warp.  The state is 27 words + 6 queue bytes per ray in shared memory; 84 rays x 4 warps x 5 blocks is the
+// most that stays under the 196 KB shared-memory carve-out, which leaves the SM 60 KB of L1 instead of 28 KB (C5 at 16
+// spp, trace ms per frame: 64 rays 384, 72 359, 80 346, 84 343, 92 382 — the step up is the carve-out — 96 385).
 #ifndef PSY_POOL_RAYS
-#define PSY_POOL_RAYS 80
+#define PSY_POOL_RAYS 84
 #endif
 constexpr int POOL_RAYS = PSY_POOL_RAYS;  // rays per warp (multiple of 4, < 256)
 constexpr int POOL_WARPS = 4;             // warps per block
@@ -67,9 +72,7 @@ enum PoolField {
     PF_MESH_PATH,
     PF_TVBASE,  // tri_verts index of triangle 0 of the current mesh, minus tri_base * 3 * keys
     PF_NK,      // vertex keys of the current mesh
-    PF_WOL,     // 3+3 words: origin and 1/direction in the root assembly's space (what leaving a first-level
-                // assembly goes back to, without a trip to the scratch area)
-    PF_STK = PF_WOL + 6,  // POOL_WIN words: ring window of the stack
+    PF_STK,  // POOL_WIN words: ring window of the stack
     PF_WORDS = PF_STK + POOL_WIN
 };
 
@@ -95,8 +98,10 @@ constexpr uint32_t PREC_CLS_SHIFT = 4;
 constexpr int POOL_CTX_WORDS = 9;
 constexpr int POOL_MS_WORDS = 12;
 constexpr int POOL_RC_WORDS = 6;  // per ray: origin in permuted axis order + shear constants of the watertight test
+constexpr int POOL_WOL_WORDS = 6;  // per ray: origin and 1/direction in the root assembly's space (written once per ray;
+                                   // what leaving a first-level assembly goes back to)
 constexpr size_t POOL_SCRATCH_WORDS_PER_WARP =
-    (size_t)(TRACE_STACK_SIZE + POOL_CTX_WORDS * TRACE_MAX_NEST + POOL_MS_WORDS + POOL_RC_WORDS) * POOL_RAYS;
+    (size_t)(TRACE_STACK_SIZE + POOL_CTX_WORDS * TRACE_MAX_NEST + POOL_MS_WORDS + POOL_RC_WORDS + POOL_WOL_WORDS) * POOL_RAYS;
 constexpr size_t POOL_SMEM_BYTES_PER_WARP = (size_t)PF_WORDS * POOL_RAYS * 4 + (size_t)Q_COUNT * POOL_RAYS;
 constexpr size_t POOL_SMEM_BYTES = POOL_SMEM_BYTES_PER_WARP * POOL_WARPS;
 
@@ -161,6 +166,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
     uint32_t* const ctxb = stk + TRACE_STACK_SIZE * R;            // saved parent spaces of nested assemblies
     uint32_t* const msb = ctxb + POOL_CTX_WORDS * TRACE_MAX_NEST * R;  // local->world of the current mesh
     uint32_t* const rcb = msb + POOL_MS_WORDS * R;                     // per-ray constants of the triangle test
+    uint32_t* const wolb = rcb + POOL_RC_WORDS * R;                    // root-space copy of the ray
     const uint32_t n_rays = *count;
 
     struct {
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
         flags = (flags & ~(RF_CTXN_MASK | RF_SPACE_MASK)) | (((flags >> RF_WSPACE_SHIFT) & 15u) << 1); \
         ST(PF_PATH_BASE, r) = 0u;                                                                   \
         ST(PF_INST_BASE, r) = S.root_instance_base;                                                 \
-        _Pragma("unroll") for (int w_ = 0; w_ < 6; ++w_) ST(PF_OL + w_, r) = ST(PF_WOL + w_, r);    \
+        _Pragma("unroll") for (int w_ = 0; w_ < 6; ++w_) ST(PF_OL + w_, r) = wolb[w_ * R + r];      \
     }
 // (popping an entry from below the mesh entry's / first-level assembly's stack height leaves it: no marker needed)
 #define PSY_POP(out)                                \
@@ -313,7 +319,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, PSY_POOL_MIN_BLOCKS)
                 ST(PF_PATH_BASE, r) = 0u;
                 ST(PF_INST_BASE, r) = S.root_instance_base;
 #pragma unroll
-                for (int w = 0; w < 6; ++w) ST(PF_WOL + w, r) = ST(PF_OL + w, r);
+                for (int w = 0; w < 6; ++w) wolb[w * R + r] = ST(PF_OL + w, r);
                 rcb[0 * R + r] = __float_as_uint(op.x), rcb[1 * R + r] = __float_as_uint(op.y);
                 rcb[2 * R + r] = __float_as_uint(op.z);
                 rcb[3 * R + r] = __float_as_uint(pre.sx), rcb[4 * R + r] = __float_as_uint(pre.sy);
