@@ -45,6 +45,13 @@ struct DMesh {
 //   bit 31 = 0 | bits 28-30: min(n_keys, 8) - 1 | bits 0-27: unit offset of the node
 // (key count code 7 = "8 or more keys": the count is then read from the header, a dependent fetch).
 // A static node is 8 units = 128 bytes, exactly the ABI's PsyBvh4Node.
+// Device-only colour kind (product build): an XYZ colour that does not vary over the shutter, with its Meng spectrum
+// interpolated over the chromaticity grid ONCE at upload (the lookup is linear in the cell's spectra,
+// meng.rs:254-272,319-320) — a = index of its 95-sample spectrum in DScene::meng_baked (as bits), b = x + y + z times
+// whatever scale has been applied since.  Shading then costs one lerp per wavelength instead of the cell search and
+// up to six spectra per wavelength.  Float-reassociated against the reference's order (~1e-7 relative), so the strict
+// build does not bake.
+constexpr uint32_t PSY_COLOR_BAKED = 3u;
 constexpr uint32_t NODE2_OFF_MASK = 0x0FFFFFFFu;
 constexpr uint32_t NODE2_KC_SHIFT = 28;
 
@@ -96,6 +103,7 @@ struct DScene {
     float world_light_energy_sum;  // fold of approximate_energy over world lights
     // spectral tables
     const float* meng_spectra;  // [186][95]
+    const float* meng_baked;    // [n baked colours][95]: see PSY_COLOR_BAKED
     uint32_t res_x, res_y;
 };
 

@@ -418,7 +418,19 @@ PSY_NOINLINE V4 color_to_spectral(const DScene& S, const PsyColor& c, float hero
 #pragma unroll
     for (int i = 0; i < 4; ++i) wls[i] = nth_wavelength(hero, i);
     V4 r;
-    if (c.kind == PSY_COLOR_XYZ) {
+    if (c.kind == PSY_COLOR_BAKED) {
+        // the colour's own spectrum, interpolated over the chromaticity grid at upload (dscene.cuh)
+        const float* __restrict__ sp = S.meng_baked + (size_t)__float_as_uint(c.a) * PSY_MENG_N;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float sb = (wls[k] - 360.0f) / (830.0f - 360.0f) * ((float)PSY_MENG_N - 1.0f);
+            const int s0 = (int)sb;
+            const int s1 = s0 + 1 < PSY_MENG_N - 1 ? s0 + 1 : PSY_MENG_N - 1;
+            const float f = sb - (float)s0;
+            r.v[k] = __ldg(sp + s0) * (1.0f - f) + __ldg(sp + s1) * f;
+        }
+        r = (r * c.b) * splat4(1.0f / PSY_MENG_EER);
+    } else if (c.kind == PSY_COLOR_XYZ) {
         r = spectrum_xyz_to_p_4(S, wls, c.a, c.b, c.c) * splat4(1.0f / PSY_MENG_EER);
     } else if (c.kind == PSY_COLOR_BLACKBODY) {
 #pragma unroll
@@ -431,7 +443,9 @@ PSY_NOINLINE V4 color_to_spectral(const DScene& S, const PsyColor& c, float hero
 }
 PSY_DEV PsyColor color_scale(const PsyColor& c, float s) {
     PsyColor r = c;
-    if (c.kind == PSY_COLOR_XYZ) {
+    if (c.kind == PSY_COLOR_BAKED) {
+        r.b = c.b * s;
+    } else if (c.kind == PSY_COLOR_XYZ) {
         r.a = c.a * s, r.b = c.b * s, r.c = c.c * s;
     } else {
         r.b = c.b * s;

@@ -192,6 +192,7 @@ struct PsyScene {
     DScene d{};
     uint32_t res_x = 0, res_y = 0, spp = 0, seed = 0;
     uint64_t upload_bytes = 0;
+    DevBuf meng_baked;
     DevBuf nodes, node_blob, motion, tri_verts, tris, normals, meshes, lights, light_shape, light_colors, objects, shaders,
         assemblies, instances, light_instances, light_inst_local, xforms, light_nodes, lt_bounds, paths, path_xforms,
         path_inv, path_recs, path_static, cam_xforms, cam_tfovs, cam_aperture, cam_focus, distant, world_floats, meng;
@@ -230,6 +231,55 @@ HXf xf_from_abi(const PsyXform& p) {
     m.Z = psyh::v3(p.r[0][2], p.r[1][2], p.r[2][2]);
     m.T = psyh::v3(p.r[0][3], p.r[1][3], p.r[2][3]);
     return m;
+}
+
+// spectrum_xyz_to_p_4 (meng.rs:177-328) evaluated AT the 95 table wavelengths for one XYZ colour: what the product
+// build interpolates once per colour at upload instead of once per shading call (PSY_COLOR_BAKED, dscene.cuh).
+// Returns false when the colour has no spectrum to bake (x + y + z = 0 or not finite: the exact path returns 0).
+bool meng_bake(float x, float y, float z, float* out95, float& inv_norm_out) {
+    const float inv_norm = x + y + z;
+    const float norm = 1.0f / inv_norm;
+    if (!(norm < 3.402823466e+38f)) return false;
+    inv_norm_out = inv_norm;
+    for (int j = 0; j < MENG_NUM_SAMPLES; ++j) out95[j] = 0.0f;
+    const float xyy0 = x * norm, xyy1 = y * norm;
+    const float uv0 = MENG_MAT_XY_TO_UV[0] * xyy0 + MENG_MAT_XY_TO_UV[1] * xyy1 + MENG_MAT_XY_TO_UV[2];
+    const float uv1 = MENG_MAT_XY_TO_UV[3] * xyy0 + MENG_MAT_XY_TO_UV[4] * xyy1 + MENG_MAT_XY_TO_UV[5];
+    if (uv0 < 0.0f || uv0 >= (float)MENG_GRID_WIDTH || uv1 < 0.0f || uv1 >= (float)MENG_GRID_HEIGHT) return true;
+    const int uvi0 = (int)uv0, uvi1 = (int)uv1;
+    const short* cell = MENG_GRID[uvi0 + MENG_GRID_WIDTH * uvi1];
+    const bool inside = cell[0] != 0;
+    const int num = cell[1];
+    if (num == 0) return true;
+    const short* idx = cell + 2;
+    if (inside) {
+        const float u2 = uv0 - (float)uvi0, v2 = uv1 - (float)uvi1;
+        for (int j = 0; j < MENG_NUM_SAMPLES; ++j)
+            out95[j] = MENG_SPECTRA[idx[0]][j] * ((1.0f - u2) * (1.0f - v2)) + MENG_SPECTRA[idx[2]][j] * ((1.0f - u2) * v2) +
+                       MENG_SPECTRA[idx[3]][j] * (u2 * v2) + MENG_SPECTRA[idx[1]][j] * (u2 * (1.0f - v2));
+        return true;
+    }
+    const float ex = uv0 - MENG_UV[idx[0]][0], ey = uv1 - MENG_UV[idx[0]][1];
+    float e0x = MENG_UV[idx[1]][0] - MENG_UV[idx[0]][0], e0y = MENG_UV[idx[1]][1] - MENG_UV[idx[0]][1];
+    float uu = e0x * ey - ex * e0y;
+    for (int i = 0; i < num - 1; ++i) {
+        const int last = (i == num - 2) ? 1 : i + 2;
+        const float e1x = MENG_UV[idx[last]][0] - MENG_UV[idx[0]][0], e1y = MENG_UV[idx[last]][1] - MENG_UV[idx[0]][1];
+        const float vv = ex * e1y - e1x * ey;
+        const float area = e0x * e1y - e1x * e0y;
+        const float u = uu / area, v = vv / area;
+        const float w = 1.0f - u - v;
+        if (u < 0.0f || v < 0.0f || w < 0.0f) {
+            uu = -vv;
+            e0x = e1x;
+            e0y = e1y;
+            continue;
+        }
+        for (int j = 0; j < MENG_NUM_SAMPLES; ++j)
+            out95[j] = MENG_SPECTRA[idx[0]][j] * w + MENG_SPECTRA[idx[i + 1]][j] * v + MENG_SPECTRA[idx[last]][j] * u;
+        break;
+    }
+    return true;
 }
 
 // TransformStack::push (transform_stack.rs:33-62): compose parent keys with child keys
@@ -1074,11 +1124,37 @@ static int32_t scene_create_one(PsyContext* ctx, const PsySceneDesc* s, PsyScene
     UP(tris, s->tris, (size_t)s->n_tris * 4);
     UP(normals, normals4.data(), normals4.size());
     UP(meshes, dmeshes.data(), dmeshes.size());
+    // Device copies of the colours; the product build bakes every XYZ colour that is constant over the shutter
+    // (shaders, single-key surface lights, the background) into its own 95-sample spectrum (PSY_COLOR_BAKED).
+    std::vector<PsyColor> dev_colors(s->light_colors, s->light_colors + s->n_light_colors);
+    std::vector<PsyShader> dev_shaders(s->shaders, s->shaders + s->n_shaders);
+    PsyColor dev_background = s->background;
+    std::vector<float> baked;
+#if !PSY_STRICT
+    {
+        auto bake = [&](PsyColor& c) {
+            if (c.kind != PSY_COLOR_XYZ) return;
+            float sp[MENG_NUM_SAMPLES], inv_norm = 0.0f;
+            if (!meng_bake(c.a, c.b, c.c, sp, inv_norm)) return;
+            const uint32_t index = (uint32_t)(baked.size() / MENG_NUM_SAMPLES);
+            baked.insert(baked.end(), sp, sp + MENG_NUM_SAMPLES);
+            c.kind = PSY_COLOR_BAKED;
+            std::memcpy(&c.a, &index, 4);
+            c.b = inv_norm;
+            c.c = 0.0f;
+        };
+        for (auto& sh : dev_shaders) bake(sh.color);
+        for (uint32_t i = 0; i < s->n_lights; ++i)
+            if (s->lights[i].n_colors == 1 && s->lights[i].color_base < dev_colors.size()) bake(dev_colors[s->lights[i].color_base]);
+        bake(dev_background);
+    }
+#endif
     UP(lights, s->lights, (size_t)s->n_lights);
     UP(light_shape, s->light_shape, (size_t)s->n_light_shape);
-    UP(light_colors, s->light_colors, (size_t)s->n_light_colors);
+    UP(light_colors, dev_colors.data(), dev_colors.size());
     UP(objects, s->objects, (size_t)s->n_objects);
-    UP(shaders, s->shaders, (size_t)s->n_shaders);
+    UP(shaders, dev_shaders.data(), dev_shaders.size());
+    UP(meng_baked, baked.data(), baked.size());
     UP(assemblies, s->assemblies, (size_t)s->n_assemblies);
     UP(instances, s->instances, (size_t)s->n_instances);
     UP(light_instances, s->light_instances, (size_t)s->n_light_instances);
@@ -1220,7 +1296,7 @@ static int32_t scene_create_one(PsyContext* ctx, const PsySceneDesc* s, PsyScene
     d.n_cam_tfovs = s->camera.n_tfovs;
     d.n_cam_aperture = s->camera.n_aperture_radii;
     d.n_cam_focus = s->camera.n_focus_distances;
-    d.background = s->background;
+    d.background = dev_background;
     d.distant_lights = sc->distant.as<PsyDistantLight>();
     d.world_floats = sc->world_floats.as<float>();
     d.n_distant_lights = s->n_distant_lights;
@@ -1240,6 +1316,7 @@ static int32_t scene_create_one(PsyContext* ctx, const PsySceneDesc* s, PsyScene
         d.world_light_energy_sum = sum;
     }
     d.meng_spectra = sc->meng.as<float>();
+    d.meng_baked = sc->meng_baked.as<float>();
     d.res_x = s->res_x;
     d.res_y = s->res_y;
     lap("texture object, DScene");
