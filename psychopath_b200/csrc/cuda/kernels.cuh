@@ -540,20 +540,24 @@ __global__ void __launch_bounds__(PSY_LIGHT_THREADS) k_shade_light(DScene S, Pat
         V3 dir = mk3(0, 0, 0);
         Isect is;
         if (on) {
-            const HitRec h = P.hits[slot];
-            const float4 ro = P.ray_o[slot], rd = P.ray_d[slot];
-            time = ro.w;
+            // the finalised hit, as k_shade_select left it (finalize_hit runs once per surface hit, there)
+            const float4 c0 = P.ic[0][slot], c1 = P.ic[1][slot], c2 = P.ic[2][slot], c4 = P.ic[4][slot], c5 = P.ic[5][slot];
+            time = P.ray_o[slot].w;
             wl = P.wavelength[slot];
-            dir = mk3(rd.x, rd.y, rd.z);
-            finalize_hit(S, h, mk3(ro.x, ro.y, ro.z), dir, time, is);
+            is.kind = PSY_HIT_TRIANGLE;
+            is.t = 0.0f, is.sample_pdf = 0.0f;
+            is.pos = mk3(c0.x, c0.y, c0.z), is.pos_err = c0.w;
+            is.nor_g = mk3(c1.x, c1.y, c1.z), is.closure.roughness = c1.w;
+            is.incoming = mk3(c2.x, c2.y, c2.z), is.closure.fresnel = c2.w;
+            is.nor = mk3(c4.x, c4.y, c4.z);
+            is.closure.kind = KIND;
+            is.closure.color.kind = __float_as_uint(c5.x), is.closure.color.a = c5.y, is.closure.color.b = c5.z;
+            is.closure.color.c = c5.w;
+            dir = is.incoming;
         }
-        __syncthreads();
         ShadeCtx shade_ctx;
         if (on) {
             shade_ctx = closure_prepare<KIND>(S, is.closure, dir, is.nor, is.nor_g, wl);
-            P.ic[0][slot] = make_float4(is.pos.x, is.pos.y, is.pos.z, is.pos_err);
-            P.ic[1][slot] = make_float4(is.nor_g.x, is.nor_g.y, is.nor_g.z, is.closure.roughness);
-            P.ic[2][slot] = make_float4(is.incoming.x, is.incoming.y, is.incoming.z, is.closure.fresnel);
             P.ic[3][slot] = to_f4(shade_ctx.spec);
             P.ic[4][slot] = make_float4(shade_ctx.nn.x, shade_ctx.nn.y, shade_ctx.nn.z, 0.0f);
             P.ic[5][slot] = make_float4(shade_ctx.fng.x, shade_ctx.fng.y, shade_ctx.fng.z, 0.0f);
@@ -628,6 +632,13 @@ __global__ void __launch_bounds__(128, 8) k_shade_select(DScene S, PathPool P, B
         select_light<KIND>(S, s4[0], ro.w, is, pick);
         P.light_pick[slot] = make_uint4(pick.kind, pick.index, pick.parent_path, __float_as_uint(pick.selection_pdf));
         P.light_uv[slot] = make_float2(s4[1], s4[2]);
+        // the finalised hit goes on to k_shade_light (and from there to k_shade_bounce): computed once per surface hit
+        P.ic[0][slot] = make_float4(is.pos.x, is.pos.y, is.pos.z, is.pos_err);
+        P.ic[1][slot] = make_float4(is.nor_g.x, is.nor_g.y, is.nor_g.z, is.closure.roughness);
+        P.ic[2][slot] = make_float4(is.incoming.x, is.incoming.y, is.incoming.z, is.closure.fresnel);
+        P.ic[4][slot] = make_float4(is.nor.x, is.nor.y, is.nor.z, 0.0f);  // (unflipped; k_shade_light replaces it)
+        P.ic[5][slot] = make_float4(__uint_as_float(is.closure.color.kind), is.closure.color.a, is.closure.color.b,
+                                    is.closure.color.c);
     }
 }
 
