@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -44,29 +45,91 @@ int32_t fail(int32_t code, const std::string& msg) {
             return fail(PSY_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));               \
     } while (0)
 
+// Freed device buffers are kept (per device, up to 8 GB) and handed out again: a renderer that uploads a scene per
+// frame (Blender, bench.py's end-to-end arm) otherwise pays for ~35 cudaMalloc per create and, now and then, for a
+// cudaFree that takes hundreds of milliseconds when the driver returns a large block to the system.
+struct BufCache {
+    std::mutex mu;
+    std::map<int, std::multimap<size_t, void*>> free_;
+    std::map<int, size_t> held;
+    static constexpr size_t LIMIT = 8ull << 30, BIGGEST = 2ull << 30;
+    void* take(int dev, size_t n, size_t& cap) {
+        std::lock_guard<std::mutex> g(mu);
+        auto& m = free_[dev];
+        auto it = m.lower_bound(n);
+        if (it == m.end() || it->first > 2 * n + (1u << 20)) return nullptr;
+        void* p = it->second;
+        cap = it->first;
+        held[dev] -= cap;
+        m.erase(it);
+        return p;
+    }
+    bool put(int dev, void* p, size_t cap) {
+        std::lock_guard<std::mutex> g(mu);
+        if (cap > BIGGEST || held[dev] + cap > LIMIT) return false;
+        free_[dev].emplace(cap, p);
+        held[dev] += cap;
+        return true;
+    }
+    void drop(int dev) {  // psy_shutdown
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& e : free_[dev]) cudaFree(e.second);
+        free_[dev].clear();
+        held[dev] = 0;
+    }
+};
+BufCache& buf_cache() {
+    static BufCache c;
+    return c;
+}
+
 struct DevBuf {
     void* p = nullptr;
-    size_t bytes = 0;
+    size_t bytes = 0;  // what the owner asked for
+    size_t cap = 0;    // what the allocation holds
+    int dev = -1;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr, o.bytes = 0; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), cap(o.cap), dev(o.dev) { o.p = nullptr, o.bytes = 0, o.cap = 0; }
     DevBuf& operator=(DevBuf&& o) noexcept {
         if (this != &o) {
-            if (p) cudaFree(p);
-            p = o.p, bytes = o.bytes;
-            o.p = nullptr, o.bytes = 0;
+            release();
+            p = o.p, bytes = o.bytes, cap = o.cap, dev = o.dev;
+            o.p = nullptr, o.bytes = 0, o.cap = 0;
         }
         return *this;
     }
-    ~DevBuf() {
-        if (p) cudaFree(p);
+    ~DevBuf() { release(); }
+    void release() {
+        if (p && !buf_cache().put(dev, p, cap)) cudaFree(p);
+        p = nullptr, bytes = 0, cap = 0;
     }
     cudaError_t alloc(size_t n) {
-        if (p) cudaFree(p);
-        p = nullptr;
+        const size_t want = n ? n : 16;
+        if (p && cap >= want && cap <= 2 * want + (1u << 20)) {
+            bytes = n;
+            return cudaSuccess;
+        }
+        release();
+        cudaGetDevice(&dev);
+        p = buf_cache().take(dev, want, cap);
+        if (!p) {
+            cap = (want + 65535) & ~(size_t)65535;
+            cudaError_t e = cudaMalloc(&p, cap);
+            if (e != cudaSuccess) {
+                // make room: give the cached buffers back to the driver and try once more
+                cudaGetLastError();
+                buf_cache().drop(dev);
+                e = cudaMalloc(&p, cap);
+            }
+            if (e != cudaSuccess) {
+                p = nullptr, cap = 0;
+                return e;
+            }
+        }
         bytes = n;
-        return cudaMalloc(&p, n ? n : 16);
+        return cudaSuccess;
     }
     template <typename T>
     cudaError_t upload(const T* src, size_t count, cudaStream_t s) {
@@ -931,6 +994,11 @@ int32_t psy_shutdown(PsyContext* ctx) {
     if (!ctx) return PSY_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    buf_cache().drop(ctx->device);
+    for (PsyContext* p : ctx->peers) {
+        cudaSetDevice(p->device);
+        buf_cache().drop(p->device);
+    }
     delete ctx;  // peers, communicators, work queue
     return PSY_OK;
 }
