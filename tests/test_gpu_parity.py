@@ -143,6 +143,18 @@ def test_image_tiling_and_determinism():
     assert st1["ray_count"] == st2["ray_count"]
     bx, _ = r.render_bucket(8, 8, 16, 16)
     assert np.array_equal(bx, img1[8:24, 8:24])
+    # page-locked host buffers (Scene.pin, render(out=...)) and the reuse of a destroyed scene's device buffers change
+    # where the bytes live, not what they are
+    scene.pin()
+    r2 = api.Renderer(scene)
+    out = r2.pinned_image()
+    img4, _ = r2.render(max_samples_per_bucket=4096, out=out)
+    assert img4 is out and np.array_equal(img1, img4)
+    r2.close()
+    r3 = api.Renderer(scene)
+    assert np.array_equal(r3.render(max_samples_per_bucket=4096)[0], img1)
+    r3.close()
+    scene.unpin()
     # crop (inclusive coordinates, renderer.rs:100-108) leaves the rest of the image untouched (zero)
     crop, _ = r.render(crop=(10, 5, 29, 20))
     assert np.array_equal(crop[5:21, 10:30], img1[5:21, 10:30])
