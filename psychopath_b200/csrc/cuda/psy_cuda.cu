@@ -847,6 +847,24 @@ int32_t render_buckets_impl(PsyScene* sc, const std::vector<Bucket>& jobs, JobFe
     if (counters) CK(cudaMemcpy(&tc, sc->counters.p, sizeof(tc), cudaMemcpyDeviceToHost));
     sc->last_trace_ms = sum_ms(ev.trace);
     sc->last_trace_launches = ev.trace.size();
+    if (getenv("PSY_WAVE_STATS") && ev.trace.size() == mine.size() * WAVES && ev.shade.size() == ev.trace.size()) {
+        // per wave over all buckets: rays, trace / shade milliseconds, rays per microsecond of the trace kernel —
+        // the evidence for or against refilling dead path slots (later waves are thinner: are they slower per ray?)
+        for (int w = 0; w < WAVES; ++w) {
+            uint64_t r = 0;
+            double tms = 0.0, sms = 0.0;
+            for (size_t k = 0; k < mine.size(); ++k) {
+                r += counts[k * COUNT_SLOTS + w];
+                float ms = 0.0f;
+                auto& pt = ev.trace[k * WAVES + w];
+                if (pt.first && pt.second && cudaEventElapsedTime(&ms, pt.first, pt.second) == cudaSuccess) tms += ms;
+                auto& ps = ev.shade[k * WAVES + w];
+                if (ps.first && ps.second && cudaEventElapsedTime(&ms, ps.first, ps.second) == cudaSuccess) sms += ms;
+            }
+            std::fprintf(stderr, "[waves] wave %d: %12llu rays  trace %9.2f ms (%7.1f Mrays/s)  shade %9.2f ms\n", w + 1,
+                         (unsigned long long)r, tms, tms > 0 ? (double)r / tms * 1e-3 : 0.0, sms);
+        }
+    }
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         stats->trace_time = sc->last_trace_ms * 1e-3;
