@@ -1007,6 +1007,7 @@ static Ray camera_ray(const PsySceneDesc& d, float x, float y, float time, float
 
 // Debug trace of one sample's path events (oracle_set_debug): prints every quantity LightPath::next derives.
 static uint32_t g_dbg_px = 0xFFFFFFFFu, g_dbg_py = 0, g_dbg_si = 0;
+static bool g_wave_stats = false;
 #define ORC_DBG(...)                                                               \
     do {                                                                           \
         if (ORC_UNLIKELY(g_debug_trace) && px == g_dbg_px && py == g_dbg_py && sample_number == g_dbg_si) { \
@@ -1224,8 +1225,15 @@ static void render_bucket(const PsySceneDesc& d, const Paths& paths, uint32_t bx
     while (pi > 0) {
         auto ta = clk::now();
         isects.resize(pi);
+        const Counters before = tracer.cnt;
         for (size_t i = 0; i < pi; ++i) isects[i] = tracer.trace(rays[i]);
         res.rays += pi;
+        if (ORC_UNLIKELY(g_wave_stats))  // oracle_set_wave_stats: per-wave visit counts (what kind of ray costs what)
+            std::fprintf(stderr, "[oracle waves] %zu rays: %.2f node visits (%.2f two-key), %.2f triangle tests, %.2f instance entries per ray\n",
+                         pi, (double)(tracer.cnt.node_visits - before.node_visits) / (double)pi,
+                         (double)(tracer.cnt.motion_node_visits - before.motion_node_visits) / (double)pi,
+                         (double)(tracer.cnt.tri_tests - before.tri_tests) / (double)pi,
+                         (double)(tracer.cnt.instance_visits - before.instance_visits) / (double)pi);
         auto tb = clk::now();
         res.trace_s += std::chrono::duration<double>(tb - ta).count();
         size_t new_end = 0;
@@ -1472,6 +1480,7 @@ int oracle_camera_rays(const PsySceneDesc* d, uint32_t x0, uint32_t y0, uint32_t
 
 //---- unit-level entry points used to pin the restatement against the reference's own tests -------
 void oracle_set_strict_math(int on) { strict_math() = on != 0; }
+void oracle_set_wave_stats(int on) { g_wave_stats = on != 0; }
 // sphere_lambert (surface_closure.rs:351-377) and the g / h terms it evaluates before branching
 float oracle_sphere_lambert(float nlcos, float rcos, float* g_h_nl_r) {
     if (g_h_nl_r) {
