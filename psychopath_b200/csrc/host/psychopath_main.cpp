@@ -32,6 +32,11 @@ int psyh_write_png(const char* path, const float* xyz, uint32_t w, uint32_t h);
 int psyh_write_exr(const char* path, const float* xyz, uint32_t w, uint32_t h);
 size_t psyh_bucket_base64(const float* xyz, uint32_t w, uint32_t h, char* out, size_t cap);
 void psyh_set_mesh_topology_builder(void* fn, void* ctx, uint32_t min_tris);
+int psyh_synth_displaced_grid(uint32_t quads_per_side, uint32_t n_vert_keys, uint32_t n_xform_keys, uint32_t res_x,
+                              uint32_t res_y, uint32_t spp, uint32_t seed, void** out);
+int psyh_synth_instanced(uint32_t asset_quads, uint32_t n_assets, uint32_t n_clusters, uint32_t inst_per_cluster,
+                         uint32_t lights_per_cluster, uint32_t cluster_xform_keys, uint32_t res_x, uint32_t res_y,
+                         uint32_t spp, uint32_t seed, uint32_t motion_pct, void** out);
 }
 
 namespace {
@@ -85,6 +90,7 @@ int main(int argc, char** argv) {
     std::vector<int> devices;  // --gpus N / --device-list a,b,c (flags the GPU host adds)
     bool counters = false, gpu_build = false;
     std::string probe_in, probe_out;
+    std::string synth;  // --synth NAME: one of BASELINE.json's synthetic configurations instead of a .psy file
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto need = [&](int n) {
@@ -127,6 +133,9 @@ int main(int argc, char** argv) {
             if (devices.empty()) die("Argument '--device-list' needs a comma-separated list of CUDA device indices");
         } else if (a == "--counters") {
             counters = true;
+        } else if (a == "--synth") {
+            need(1);
+            synth = argv[++i];
         } else if (a == "--gpu-build") {
             gpu_build = true;  // mesh BVH order + topology from the GPU LBVH build
         } else if (a == "--probe-rays") {
@@ -152,12 +161,17 @@ int main(int argc, char** argv) {
                     sizeof(PsyHit), sizeof(PsyRay));
         return 0;
     }
-    if (!has_input && !use_stdin) die("error: The following required arguments were not provided: --input <FILE>");
+    if (!has_input && !use_stdin && synth.empty())
+        die("error: The following required arguments were not provided: --input <FILE>");
+    if (!synth.empty() && synth != "C3" && synth != "C4" && synth != "C5" && synth != "C5r1" && synth != "tiny")
+        die("Argument '--synth': one of C3, C4, C5, C5r1, tiny");
 
     Timer t;
     if (!serialized) std::printf("Parsing scene file...\n");
     std::string text;
-    if (use_stdin) {
+    if (!synth.empty()) {
+        // (nothing to parse: the scene is generated below)
+    } else if (use_stdin) {
         // main.rs:194-226: read until the "__PSY_EOF__" marker
         std::string chunk(4096, '\0');
         for (;;) {
@@ -180,7 +194,10 @@ int main(int argc, char** argv) {
         text = ss.str();
     }
     uint32_t n_scenes = 0;
-    if (psyh_count_scenes(text.c_str(), &n_scenes) != 0) die(std::string("Parse error: ") + psyh_last_error());
+    if (!synth.empty())
+        n_scenes = 1;
+    else if (psyh_count_scenes(text.c_str(), &n_scenes) != 0)
+        die(std::string("Parse error: ") + psyh_last_error());
     if (!serialized) std::printf("\tParsed scene file in %.3fs\n", t.tick());
 
     PsyContext* ctx = nullptr;
@@ -194,7 +211,29 @@ int main(int argc, char** argv) {
         t.tick();
         if (!serialized) std::printf("Building scene...\n");
         void* hs = nullptr;
-        if (psyh_load_psy_string(text.c_str(), si, &hs) != 0) die(std::string("Parse error: ") + psyh_last_error());
+        if (!synth.empty()) {
+            // BASELINE.json's synthetic configurations, generated straight into the flat scene:
+            //   C3  10 M-triangle displaced mesh, 4 deformation + 4 transform keys, 1920x1080, 128 spp
+            //   C4  100 clusters x (10 instances of 4 x 500k-triangle assets + 10 area lights), 1920x1080, 64 spp
+            //   C5  the same with moving clusters (motion-blurred BVH nodes), 3840x2160, 256 spp   (C5r1: round 1's motion)
+            //   tiny  a small instanced scene for tests, 320x180, 8 spp
+            int rc = 1;
+            if (synth == "C3")
+                rc = psyh_synth_displaced_grid(2240, 4, 4, 1920, 1080, 128, 3, &hs);
+            else if (synth == "C4")
+                rc = psyh_synth_instanced(500, 4, 100, 10, 10, 1, 1920, 1080, 64, 4, 100, &hs);
+            else if (synth == "C5")
+                rc = psyh_synth_instanced(500, 4, 100, 10, 10, 2, 3840, 2160, 256, 5, 1250, &hs);
+            else if (synth == "C5r1")
+                rc = psyh_synth_instanced(500, 4, 100, 10, 10, 2, 3840, 2160, 256, 5, 100, &hs);
+            else if (synth == "tiny")
+                rc = psyh_synth_instanced(40, 4, 16, 6, 4, 2, 320, 180, 8, 5, 1250, &hs);
+            else
+                die("Argument '--synth': one of C3, C4, C5, C5r1, tiny");
+            if (rc != 0) die(std::string("Scene generation failed: ") + psyh_last_error());
+        } else if (psyh_load_psy_string(text.c_str(), si, &hs) != 0) {
+            die(std::string("Parse error: ") + psyh_last_error());
+        }
         const PsySceneDesc* desc = psyh_scene_desc(hs);
         if (spp) {
             if (!serialized) std::printf("\tOverriding scene spp: %u\n", spp);
@@ -234,9 +273,9 @@ int main(int argc, char** argv) {
         params.crop_x1 = crop[0], params.crop_y1 = crop[1], params.crop_x2 = crop[2], params.crop_y2 = crop[3];
         // --spb on the reference bounds the paths in flight per thread (default 4096); on the GPU the same
         // knob sizes the device path pool, whose default is much larger.
-        // (without --spb: 4 Mi-path buckets when Blender displays them as they arrive, else as large as the library
-        // allows — the later waves of small buckets cannot fill the GPU)
-        params.max_samples_per_bucket = spb ? spb : (serialized ? (4u << 20) : (64u << 20));
+        // (without --spb the library chooses: the whole image up to 64 Mi paths on one GPU, 12 buckets per GPU when the
+        // image is shared, 4 Mi-path buckets when Blender displays them as they arrive)
+        params.max_samples_per_bucket = spb;  // 0 = the library's default for the number of GPUs / streaming
         params.collect_counters = (stats || counters) ? 1u : 0u;
         std::vector<float> image((size_t)desc->res_x * desc->res_y * 3);
         PsyStats rs;

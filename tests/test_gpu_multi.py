@@ -71,3 +71,32 @@ def test_cli_probe_rays(tmp_path):
     assert len(hits) == len(rays)
     for k in ("kind", "prim_id", "inst_id", "t"):
         assert np.array_equal(hits[k], oh[k]), k
+
+
+def test_cli_renders_a_synthetic_baseline_scene(tmp_path):
+    """`psychopath --synth NAME [--gpus N]`: BASELINE.json's synthetic configurations from the command line (C5 is the
+    4K motion-blurred instanced scene of the north star; `tiny` has its structure at test size).  The picture must be
+    the one the API renders for the same scene, on one GPU and — when there are two — on two."""
+    import cv2
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(repo, "bin", "psychopath")
+    runs = [["--gpus", "1"]] + ([["--gpus", "2"]] if n_gpus() >= 2 else [])
+    imgs = []
+    for flags in runs:
+        out = subprocess.run([exe, "--synth", "tiny", "--counters"] + flags, cwd=tmp_path, capture_output=True, text=True,
+                             timeout=300)
+        assert out.returncode == 0, out.stderr
+        assert "two time keys" in out.stdout
+        imgs.append(cv2.imread(str(tmp_path / "synth_instanced.png")))
+    assert imgs[0] is not None and imgs[0].shape[:2] == (180, 320) and imgs[0].mean() > 2
+    for im in imgs[1:]:
+        assert np.array_equal(imgs[0], im)
+    scene = api.Scene.synth_instanced(asset_quads=40, n_assets=4, n_clusters=16, inst_per_cluster=6, lights_per_cluster=4,
+                                      cluster_xform_keys=2, res=(320, 180), spp=8, seed=5, motion_pct=1250)
+    xyz, _ = api.Renderer(scene).render()
+    m = np.array([[2.6896551724, -1.2758620690, -0.4137931034], [-1.0221081721, 1.9782866167, 0.0438215555],
+                  [0.0612244898, -0.2244897959, 1.1632653061]], dtype=np.float32)
+    rgb = np.clip(xyz @ m.T, 0, None)
+    srgb = np.where(rgb < 0.0031308, rgb * 12.92, 1.055 * np.power(np.maximum(rgb, 1e-12), 1 / 2.4) - 0.055)
+    want = (np.clip(srgb, 0, 1) * 255).astype(np.int32)
+    assert np.abs(imgs[0][..., ::-1].astype(np.int32) - want).mean() < 0.5
