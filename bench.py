@@ -477,6 +477,14 @@ def main():
                 "c3": c3}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
+        if rank == 0 and wq_key:
+            # remove the shared-memory work counter's name (the library unlinks it when a handle is closed)
+            import ctypes
+            lib = api.cuda_lib()
+            h = ctypes.c_void_p()
+            if lib.psy_work_queue_open(wq_key, ctypes.byref(h)) == 0:
+                lib.psy_work_queue_close(h)
         dist.destroy_process_group()
     return 0
 
