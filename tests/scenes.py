@@ -176,3 +176,166 @@ Scene $nested {
     }
 }
 """
+
+
+def random_scene_text(seed):
+    """A seeded random scene in the reference's text format, for the fuzz parity tests: every feature the path reads
+    (time keys on cameras, vertices, normals, transforms, light sizes and colours; Lambert / GGX / Emit shaders;
+    rec709 / blackbody / color_temperature colours; sphere, rectangle and distant lights; assemblies nested up to
+    three deep, instanced with and without transforms) in combinations nobody wrote by hand."""
+    import random
+    rnd = random.Random(seed)
+
+    def f(x):
+        return f"{x:.6g}"
+
+    def xform(scale=None, spread=4.0, z=None):
+        a = rnd.uniform(0, 2 * math.pi)
+        s = scale if scale is not None else rnd.uniform(0.5, 1.3)
+        c, sn = math.cos(a) * s, math.sin(a) * s
+        tx, ty = rnd.uniform(-spread, spread), rnd.uniform(-spread, spread)
+        tz = rnd.uniform(-0.2, 0.6) if z is None else z
+        return [c, sn, 0, 0, -sn, c, 0, 0, 0, 0, s, 0, tx, ty, tz, 1]
+
+    def xform_keys(n, **kw):
+        base = xform(**kw)
+        keys = [base]
+        for _ in range(n - 1):
+            k = list(keys[-1])
+            k[12] += rnd.uniform(-0.4, 0.4)
+            k[13] += rnd.uniform(-0.4, 0.4)
+            k[14] += rnd.uniform(-0.2, 0.2)
+            if rnd.random() < 0.5:  # a little extra rotation between keys
+                a = rnd.uniform(-0.15, 0.15)
+                c, s = math.cos(a), math.sin(a)
+                k[0], k[1], k[4], k[5] = k[0] * c - k[1] * s, k[0] * s + k[1] * c, k[4] * c - k[5] * s, k[4] * s + k[5] * c
+            keys.append(k)
+        return "".join(" Transform [" + " ".join(f(v) for v in k) + "]" for k in keys)
+
+    def colour(lo, hi):
+        kind = rnd.choice(["rec709", "rec709", "rec709", "blackbody", "color_temperature"])
+        if kind == "rec709":
+            return "[rec709, " + " ".join(f(rnd.uniform(lo, hi)) for _ in range(3)) + "]"
+        if kind == "blackbody":  # un-normalised Planck radiance: tiny factors
+            return f"[blackbody, {f(rnd.uniform(2500, 7000))} {f(rnd.uniform(lo, hi) * 1e-9)}]"
+        return f"[color_temperature, {f(rnd.uniform(2500, 9000))} {f(rnd.uniform(lo, hi))}]"
+
+    def shader(name):
+        kind = rnd.choice(["Lambert", "Lambert", "GGX", "GGX", "Emit"])
+        if kind == "Lambert":
+            return f"SurfaceShader ${name} {{ Type [Lambert] Color {colour(0.1, 0.9)} }}"
+        if kind == "GGX":
+            return (f"SurfaceShader ${name} {{ Type [GGX] Color {colour(0.2, 0.95)} Roughness [{f(rnd.uniform(0.02, 0.9))}] "
+                    f"Fresnel [{f(rnd.uniform(0.0, 1.0))}] }}")
+        return f"SurfaceShader ${name} {{ Type [Emit] Color {colour(0.2, 2.0)} }}"
+
+    def mesh(name):
+        n_keys = rnd.choice([1, 1, 2, 3])
+        with_normals = rnd.random() < 0.4
+        kind = rnd.choice(["patch", "patch", "box", "fan"])
+        if kind == "patch":
+            n = rnd.randint(2, 7)
+            size = rnd.uniform(0.8, 2.5)
+            base = [[(i / n - 0.5) * size, (j / n - 0.5) * size, rnd.uniform(0, 0.5)] for j in range(n + 1)
+                    for i in range(n + 1)]
+            counts, idx = [], []
+            for j in range(n):
+                for i in range(n):
+                    a, b, c, d = j * (n + 1) + i, j * (n + 1) + i + 1, (j + 1) * (n + 1) + i + 1, (j + 1) * (n + 1) + i
+                    if rnd.random() < 0.3:  # two triangles instead of a quad
+                        counts += [3, 3]
+                        idx += [a, b, c, a, c, d]
+                    else:
+                        counts.append(4)
+                        idx += [a, b, c, d]
+        elif kind == "box":
+            sx, sy, sz = (rnd.uniform(0.3, 1.0) for _ in range(3))
+            base = [[x * sx, y * sy, z * sz] for z in (0, 1) for (x, y) in ((-1, -1), (1, -1), (1, 1), (-1, 1))]
+            counts = [4] * 6
+            idx = [0, 3, 2, 1, 4, 5, 6, 7, 0, 1, 5, 4, 1, 2, 6, 5, 2, 3, 7, 6, 3, 0, 4, 7]
+        else:  # an n-gon fan around an apex (polygons of more than four vertices are fanned by the loader)
+            n = rnd.randint(5, 9)
+            r = rnd.uniform(0.5, 1.5)
+            base = [[r * math.cos(2 * math.pi * i / n), r * math.sin(2 * math.pi * i / n), 0.0] for i in range(n)]
+            base.append([0.0, 0.0, rnd.uniform(0.5, 1.8)])
+            counts = [n] + [3] * n
+            idx = list(range(n))
+            for i in range(n):
+                idx += [i, (i + 1) % n, n]
+        out = [f"MeshSurface ${name} {{"]
+        verts = base
+        for k in range(n_keys):
+            if k:
+                verts = [[v[0] + rnd.uniform(-0.08, 0.08), v[1] + rnd.uniform(-0.08, 0.08), v[2] + rnd.uniform(-0.08, 0.08)]
+                         for v in verts]
+            out.append("    Vertices [" + "  ".join(" ".join(f(c) for c in v) for v in verts) + "]")
+        if with_normals:
+            for k in range(n_keys):
+                out.append("    Normals [" + "  ".join(
+                    " ".join(f(c) for c in (rnd.uniform(-0.3, 0.3), rnd.uniform(-0.3, 0.3), 1.0)) for _ in base) + "]")
+        out.append("    FaceVertCounts [" + " ".join(map(str, counts)) + "]")
+        out.append("    FaceVertIndices [" + " ".join(map(str, idx)) + "]")
+        out.append("}")
+        return "\n".join(out)
+
+    def light(name):
+        n_keys = rnd.choice([1, 1, 2])
+        cols = " ".join(f"Color {colour(4, 40)}" for _ in range(rnd.choice([1, 1, 2])))
+        if rnd.random() < 0.5:
+            return f"SphereLight ${name} {{ {cols} " + " ".join(f"Radius [{f(rnd.uniform(0.05, 0.5))}]" for _ in range(n_keys)) + " }"
+        return f"RectangleLight ${name} {{ {cols} " + " ".join(
+            f"Dimensions [{f(rnd.uniform(0.3, 2.0))} {f(rnd.uniform(0.3, 2.0))}]" for _ in range(n_keys)) + " }"
+
+    counter = [0]
+
+    def assembly(depth, indent):
+        """The body of an assembly: shaders, meshes, lights, sub-assemblies, then the instances of all of them."""
+        counter[0] += 1
+        tag = counter[0]
+        lines, things, shaders = [], [], []
+        for i in range(rnd.randint(1, 3)):
+            shaders.append(f"sh{tag}_{i}")
+            lines.append(shader(shaders[-1]))
+        for i in range(rnd.randint(1, 3)):
+            things.append((f"m{tag}_{i}", "mesh"))
+            lines.append(mesh(things[-1][0]))
+        for i in range(rnd.randint(0 if depth else 1, 2)):
+            things.append((f"l{tag}_{i}", "light"))
+            lines.append(light(things[-1][0]))
+        if depth < 2:
+            for i in range(rnd.randint(0, 2) if depth else rnd.randint(1, 2)):
+                name = f"a{tag}_{i}"
+                things.append((name, "assembly"))
+                lines.append(f"Assembly ${name} {{\n" + assembly(depth + 1, indent + "    ") + "\n}")
+        spread = 4.0 if depth == 0 else 1.5
+        for name, kind in things:
+            for _ in range(rnd.randint(1, 3 if kind != "light" else 2)):
+                n_keys = rnd.choice([0, 1, 1, 2, 3])
+                bind = f" SurfaceShaderBind [${rnd.choice(shaders)}]" if kind == "mesh" else ""
+                z = -rnd.uniform(1.5, 4.0) if kind == "light" else None  # (the fixtures' "up" is -z in instance space)
+                xf = xform_keys(n_keys, spread=spread, z=z, scale=1.0 if kind == "light" else None) if n_keys else ""
+                lines.append(f"Instance {{ Data [${name}]{bind}{xf} }}")
+        return "\n".join(indent + ln for block in lines for ln in block.split("\n"))
+
+    cam_keys = rnd.choice([1, 2, 3])
+    cam = []
+    for k in range(cam_keys):
+        cam.append(f"        Transform [1 0 0 0  0 0 1 0  0 1 0 0  {f(0.15 * k)} {f(-11 + 0.1 * k)} {f(2.5 + 0.05 * k)} 1]")
+    fovs = "\n".join(f"        Fov [{f(rnd.uniform(40, 60))}]" for _ in range(rnd.choice([1, 2])))
+    world = [f"        BackgroundShader {{ Type [Color] Color {colour(0.02, 0.3)} }}"]
+    for i in range(rnd.randint(0, 2)):
+        n = rnd.choice([1, 2])
+        world.append(f"        DistantDiskLight $sun{i} {{ "
+                     + " ".join(f"Direction [{f(rnd.uniform(-0.5, 0.5))} {f(rnd.uniform(-0.5, 0.5))} -0.8]" for _ in range(n))
+                     + " " + " ".join(f"Color {colour(0.5, 2.0)}" for _ in range(rnd.choice([1, 2])))
+                     + " " + " ".join(f"Radius [{f(rnd.uniform(0.01, 0.2))}]" for _ in range(n)) + " }")
+    floor = ("        SurfaceShader $floor_sh { Type [Lambert] Color [rec709, 0.5 0.5 0.5] }\n"
+             "        MeshSurface $floor {\n            Vertices [-9 -9 0  9 -9 0  9 9 0  -9 9 0]\n"
+             "            FaceVertCounts [4]\n            FaceVertIndices [0 1 2 3]\n        }\n"
+             "        Instance { Data [$floor] SurfaceShaderBind [$floor_sh] }\n")
+    return (f"Scene $fuzz{seed} {{\n    Output {{ Path [\"fuzz{seed}.png\"] }}\n"
+            f"    RenderSettings {{ Resolution [64 48] SamplesPerPixel [4] Seed [{seed + 1}] }}\n"
+            f"    Camera {{\n{fovs}\n        FocalDistance [{f(rnd.uniform(8, 13))}]\n"
+            f"        ApertureRadius [{f(rnd.choice([0.0, 0.03, 0.1]))}]\n" + "\n".join(cam) + "\n    }\n"
+            "    World {\n" + "\n".join(world) + "\n    }\n"
+            "    Assembly {\n" + floor + assembly(0, "        ") + "\n    }\n}\n")
