@@ -162,7 +162,7 @@ CUDA_SYMBOLS = [
     "psy_trace_rays", "psy_render_bucket", "psy_render_bucket_samples", "psy_render_image",
     "psy_render_image_shard", "psy_device_image", "psy_scene_stream", "psy_fetch_image", "psy_last_trace_timing",
     "psy_work_queue_open", "psy_work_queue_pull", "psy_work_queue_close", "psy_build_mesh_topology",
-    "psy_host_register", "psy_host_unregister",
+    "psy_host_register", "psy_host_unregister", "psy_mesh_bvh_build", "psy_mesh_bvh_take",
 ]
 
 
@@ -190,6 +190,8 @@ def load_host():
     lib.psyh_bucket_list.restype = u32
     lib.psyh_set_mesh_topology_builder.argtypes = [C.c_void_p, C.c_void_p, u32]
     lib.psyh_set_mesh_topology_builder.restype = None
+    lib.psyh_set_mesh_bvh_builder.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u32]
+    lib.psyh_set_mesh_bvh_builder.restype = None
     lib.psyh_take_mesh_topology_seconds.argtypes = [C.POINTER(u32)]
     lib.psyh_take_mesh_topology_seconds.restype = C.c_double
     return lib

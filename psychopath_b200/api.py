@@ -43,18 +43,27 @@ class PsyError(RuntimeError):
     pass
 
 
-def enable_gpu_build(min_tris=1 << 20, device=0):
-    """meshes of at least `min_tris` triangles get their triangle order and BVH topology from the GPU
-    LBVH build (psy_build_mesh_topology) instead of the host's SAH builder; bounds and the BVH4 collapse stay as
-    they are.  Scenes built afterwards (Scene.from_* / synth_*) use it; disable_gpu_build() restores the SAH builder."""
+def enable_gpu_build(min_tris=1 << 20, device=0, mode="bvh4"):
+    """meshes of at least `min_tris` triangles are built on the GPU instead of by the host's SAH builder.
+    mode "bvh4": the whole BVH4 of the mesh (LBVH topology, time-sampled bounds, union rule, BVH4 collapse:
+    psy_mesh_bvh_build); the host only reorders the triangle list and appends the nodes.  mode "topology": triangle
+    order and binary topology only (psy_build_mesh_topology), bounds and collapse on the host — the same nodes, bit
+    for bit.  Scenes built afterwards (Scene.from_* / synth_*) use it; disable_gpu_build() restores the SAH builder."""
     lib = cuda_lib()
     ctx = _context(device)
-    fn = C.cast(lib.psy_build_mesh_topology, C.c_void_p)
-    host_lib().psyh_set_mesh_topology_builder(fn, ctx, int(min_tris))
+    if mode not in ("bvh4", "topology"):
+        raise ValueError(mode)
+    host_lib().psyh_set_mesh_topology_builder(C.cast(lib.psy_build_mesh_topology, C.c_void_p), ctx, int(min_tris))
+    if mode == "bvh4":
+        host_lib().psyh_set_mesh_bvh_builder(C.cast(lib.psy_mesh_bvh_build, C.c_void_p),
+                                             C.cast(lib.psy_mesh_bvh_take, C.c_void_p), ctx, int(min_tris))
+    else:
+        host_lib().psyh_set_mesh_bvh_builder(None, None, None, 0)
 
 
 def disable_gpu_build():
     host_lib().psyh_set_mesh_topology_builder(None, None, 0)
+    host_lib().psyh_set_mesh_bvh_builder(None, None, None, 0)
 
 
 def gpu_build_seconds():

@@ -195,4 +195,256 @@ __global__ void __launch_bounds__(256) k_lbvh_depth(const int32_t* __restrict__ 
     if ((threadIdx.x & 31u) == 0u && dep) atomicMax(depth, dep);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The rest of a mesh BVH on the device (psy_mesh_bvh_build): time-sampled bounds of every node of the binary tree,
+// the 1.4x union rule, the BVH2 -> BVH4 collapse and the traversal codes, in the host builder's arithmetic
+// (csrc/host/bvh_build.h: TopologyBoundsBuilder, bvh4_make_node; reference bvh_base.rs:96-215, bvh4.rs:186-358), so
+// that the same topology gives the same nodes bit for bit whichever side built them (tests/test_gpu_build.py).
+//
+// Every node of the binary tree has either one bounds key or the mesh's n_keys (a leaf unions its triangles key by
+// key; a parent merges two children of 1 or n keys; the union rule then keeps all keys or one).  The bounds of a
+// node are stored AT ITS PARENT (cb[parent][side][key]): the collapse reads the children of a node together.
+
+constexpr int BUILD_MAX_KEYS = 8;  // more time samples than this: the host builds the mesh
+
+struct BBox6 {
+    float mn[3], mx[3];
+};
+// SSE minps / maxps (hmath.h: sse_min, sse_max): the second operand unless the first is strictly smaller / larger
+PSY_DEV float b_min(float a, float b) { return a < b ? a : b; }
+PSY_DEV float b_max(float a, float b) { return a > b ? a : b; }
+PSY_DEV BBox6 b_empty() {
+    BBox6 b;
+    for (int d = 0; d < 3; ++d) b.mn[d] = CUDART_INF_F, b.mx[d] = -CUDART_INF_F;
+    return b;
+}
+PSY_DEV BBox6 b_union(const BBox6& a, const BBox6& b) {
+    BBox6 o;
+    for (int d = 0; d < 3; ++d) o.mn[d] = b_min(a.mn[d], b.mn[d]), o.mx[d] = b_max(a.mx[d], b.mx[d]);
+    return o;
+}
+PSY_DEV float b_area(const BBox6& b) {
+    const float dx = b.mx[0] - b.mn[0], dy = b.mx[1] - b.mn[1], dz = b.mx[2] - b.mn[2];
+    return ((dx * dy) + (dy * dz) + (dz * dx)) * 2.0f;
+}
+PSY_DEV BBox6 b_lerp(const BBox6& a, const BBox6& b, float alpha) {
+    BBox6 o;
+    for (int d = 0; d < 3; ++d) {
+        o.mn[d] = (a.mn[d] * (1.0f - alpha)) + (b.mn[d] * alpha);
+        o.mx[d] = (a.mx[d] * (1.0f - alpha)) + (b.mx[d] * alpha);
+    }
+    return o;
+}
+PSY_DEV BBox6 b_load(const float* p) {  // (written by another thread of this launch: read through L2)
+    BBox6 b;
+    for (int d = 0; d < 3; ++d) b.mn[d] = __ldcg(p + d), b.mx[d] = __ldcg(p + 3 + d);
+    return b;
+}
+PSY_DEV void b_store(float* p, const BBox6& b) {
+    for (int d = 0; d < 3; ++d) p[d] = b.mn[d], p[3 + d] = b.mx[d];
+}
+// lerp_slice (lerp.rs:20-35) over n stored keys
+PSY_DEV BBox6 b_lerp_slice(const float* keys, uint32_t n, float alpha) {
+    if (n == 1u || alpha == 1.0f) return b_load(keys + 6 * (size_t)(n - 1u));
+    const float tmp = alpha * (float)(n - 1u);
+    const uint32_t i1 = (uint32_t)tmp;
+    const float alpha2 = tmp - (float)i1;
+    return b_lerp(b_load(keys + 6 * (size_t)i1), b_load(keys + 6 * (size_t)(i1 + 1u)), alpha2);
+}
+// push_collapsed: one key (the union) when the union's area is at most 1.4x the keys' average area (bvh_base.rs:119-132)
+PSY_DEV uint32_t b_collapse(BBox6* keys, uint32_t n) {
+    BBox6 u = b_empty();
+    for (uint32_t k = 0; k < n; ++k) u = b_union(u, keys[k]);
+    float area = 0.0f;
+    for (uint32_t k = 0; k < n; ++k) area = area + b_area(keys[k]);
+    const float average_area = area / (float)n;
+    if (b_area(u) <= (average_area * 1.4f)) {
+        keys[0] = u;
+        return 1u;
+    }
+    return n;
+}
+
+// parent[c] = 2 * parent + side for every internal node but the root (-1)
+__global__ void __launch_bounds__(256) k_b2_parents(const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                                    int n_int, int32_t* __restrict__ parent) {
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= n_int) return;
+    if (i == 0) parent[0] = -1;
+    const int32_t cl = left[i], cr = right[i];
+    if (cl >= 0) parent[cl] = 2 * i;
+    if (cr >= 0) parent[cr] = 2 * i + 1;
+}
+
+// Bottom-up: one thread per leaf reference computes the leaf's bounds and climbs; at every node the second child to
+// arrive merges the two children, applies the union rule and goes on (Karras 2012, section 4).
+__global__ void __launch_bounds__(128) k_b2_refit(const float* __restrict__ verts, uint32_t n_keys,
+                                                  const uint32_t* __restrict__ tri_idx, const uint32_t* __restrict__ order,
+                                                  const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                                  const int32_t* __restrict__ parent, int n_int, float* cb, uint8_t* cnk,
+                                                  uint32_t* ready, float* root_bounds, uint32_t* root_nk) {
+    const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (t >= 2 * n_int) return;
+    int i = t >> 1, side = t & 1;
+    const int32_t c = side ? right[i] : left[i];
+    if (c >= 0) return;
+    const uint32_t code = (uint32_t)~c, first = code >> 2, count = code & 3u;
+    BBox6 keys[BUILD_MAX_KEYS];
+    for (uint32_t k = 0; k < n_keys; ++k) keys[k] = b_empty();
+    for (uint32_t j = first; j < first + count; ++j) {
+        const uint32_t tri = order[j];
+        const uint32_t v0 = tri_idx[3 * (size_t)tri], v1 = tri_idx[3 * (size_t)tri + 1], v2 = tri_idx[3 * (size_t)tri + 2];
+        for (uint32_t k = 0; k < n_keys; ++k) {
+            const float* p0 = verts + ((size_t)v0 * n_keys + k) * 3;
+            const float* p1 = verts + ((size_t)v1 * n_keys + k) * 3;
+            const float* p2 = verts + ((size_t)v2 * n_keys + k) * 3;
+            BBox6 b;  // vmin(p0, vmin(p1, p2)) (triangle_mesh.rs:86-99)
+            for (int d = 0; d < 3; ++d) b.mn[d] = b_min(p0[d], b_min(p1[d], p2[d])), b.mx[d] = b_max(p0[d], b_max(p1[d], p2[d]));
+            keys[k] = b_union(keys[k], b);
+        }
+    }
+    uint32_t nk = b_collapse(keys, n_keys);
+    for (;;) {
+        float* dst = cb + ((size_t)i * 2 + side) * n_keys * 6;
+        for (uint32_t k = 0; k < nk; ++k) b_store(dst + 6 * k, keys[k]);
+        cnk[(size_t)i * 2 + side] = (uint8_t)nk;
+        __threadfence();
+        if (atomicAdd(ready + i, 1u) == 0u) return;  // the sibling has not arrived: it will do the rest
+        __threadfence();
+        // merge_slices_append(c0, c1, union) (algorithm.rs:234-262)
+        const float* s1 = cb + ((size_t)i * 2) * n_keys * 6;
+        const float* s2 = cb + ((size_t)i * 2 + 1) * n_keys * 6;
+        const uint32_t n1 = ((volatile uint8_t*)cnk)[(size_t)i * 2], n2 = ((volatile uint8_t*)cnk)[(size_t)i * 2 + 1];
+        if (n1 == n2) {
+            nk = n1;
+            for (uint32_t k = 0; k < nk; ++k) keys[k] = b_union(b_load(s1 + 6 * k), b_load(s2 + 6 * k));
+        } else if (n1 > n2) {
+            nk = n1;
+            const float s = (float)(n1 - 1u);
+            for (uint32_t k = 0; k < nk; ++k) keys[k] = b_union(b_load(s1 + 6 * k), b_lerp_slice(s2, n2, (float)k / s));
+        } else {
+            nk = n2;
+            const float s = (float)(n2 - 1u);
+            for (uint32_t k = 0; k < nk; ++k) keys[k] = b_union(b_lerp_slice(s1, n1, (float)k / s), b_load(s2 + 6 * k));
+        }
+        nk = b_collapse(keys, nk);
+        const int32_t p = parent[i];
+        if (p < 0) {
+            for (uint32_t k = 0; k < nk; ++k) b_store(root_bounds + 6 * k, keys[k]);
+            *root_nk = nk;
+            return;
+        }
+        i = p >> 1, side = p & 1;
+    }
+}
+
+// construct_from_base takes a node's grandchildren wherever its children are internal: the BVH4 nodes are the
+// internal nodes at even depth.  mcount = the motion keys the node will append (its longest child, if that is > 1).
+__global__ void __launch_bounds__(256) k_b4_mark(const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                                 const int32_t* __restrict__ parent, const uint8_t* __restrict__ cnk,
+                                                 int n_int, uint32_t* __restrict__ is4, uint32_t* __restrict__ mcount) {
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= n_int) return;
+    uint32_t depth = 0;
+    for (int32_t p = parent[i]; p >= 0; p = parent[p >> 1]) ++depth;
+    const uint32_t mine = (depth & 1u) ? 0u : 1u;
+    is4[i] = mine;
+    uint32_t len = 0;
+    if (mine) {
+        const int32_t cs[2] = {left[i], right[i]};
+        for (int s = 0; s < 2; ++s) {
+            if (cs[s] >= 0)
+                len = max(len, (uint32_t)max(cnk[(size_t)cs[s] * 2], cnk[(size_t)cs[s] * 2 + 1]));
+            else
+                len = max(len, (uint32_t)cnk[(size_t)i * 2 + s]);
+        }
+    }
+    mcount[i] = len >= 2u ? len : 0u;
+}
+
+PSY_DEV uint32_t b4_traversal_code(int kind, uint32_t top, uint32_t a, uint32_t b) {
+    // calc_traversal_code (sub_crates/bvh_order/src/lib.rs:30-37): 0 Full 1 Left 2 Right 3 TopOnly
+    switch (kind) {
+        case 0: return top + a * 3u + b * 9u;
+        case 1: return top + a * 3u + 27u;
+        case 2: return top + a * 3u + (27u + 9u);
+        default: return top + (27u + 9u + 9u);
+    }
+}
+
+// bvh4_make_node per BVH4 node: children, traversal code, time-sampled child bounds, child references
+__global__ void __launch_bounds__(128) k_b4_emit(const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                                 const uint8_t* __restrict__ axis, const float* __restrict__ cb,
+                                                 const uint8_t* __restrict__ cnk, const uint32_t* __restrict__ is4,
+                                                 const uint32_t* __restrict__ idx4, const uint32_t* __restrict__ kbase,
+                                                 int n_int, uint32_t n_keys, uint32_t obj_base, PsyBvh4Node* __restrict__ nodes,
+                                                 PsyBBox4* __restrict__ motion) {
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= n_int || !is4[i]) return;
+    const int32_t cl = left[i], cr = right[i];
+    int32_t ref[4] = {0, 0, 0, 0};
+    const float* bp[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t nk[4] = {0, 0, 0, 0};
+    int cc = 0;
+    const size_t stride = (size_t)n_keys * 6;
+    auto take = [&](int node, int side) {
+        ref[cc] = side ? right[node] : left[node];
+        bp[cc] = cb + ((size_t)node * 2 + side) * stride;
+        nk[cc] = cnk[(size_t)node * 2 + side];
+        ++cc;
+    };
+    uint32_t code;
+    if (cl >= 0) {
+        take(cl, 0), take(cl, 1);
+        if (cr >= 0) {
+            take(cr, 0), take(cr, 1);
+            code = b4_traversal_code(0, axis[i], axis[cl], axis[cr]);
+        } else {
+            take(i, 1);
+            code = b4_traversal_code(1, axis[i], axis[cl], 0);
+        }
+    } else {
+        take(i, 0);
+        if (cr >= 0) {
+            take(cr, 0), take(cr, 1);
+            code = b4_traversal_code(2, axis[i], axis[cr], 0);
+        } else {
+            take(i, 1);
+            code = b4_traversal_code(3, axis[i], 0, 0);
+        }
+    }
+    uint32_t len = 0;
+    for (int j = 0; j < cc; ++j) len = max(len, nk[j]);
+    PsyBvh4Node nd;
+    nd.traversal_code = code;
+    nd.n_children = (uint32_t)cc;
+    nd.n_keys = len;
+    nd.key_base = len >= 2u ? kbase[i] : 0u;
+    for (int j = 0; j < 4; ++j) {
+        if (j >= cc) {
+            nd.child[j] = PSY_NONE;
+        } else if (ref[j] < 0) {
+            const uint32_t lc = (uint32_t)~ref[j];
+            nd.child[j] = PSY_CHILD_LEAF(obj_base + (lc >> 2), lc & 3u);
+        } else {
+            nd.child[j] = idx4[ref[j]];
+        }
+    }
+    const uint32_t n_out = len >= 2u ? len : 1u;
+    for (uint32_t k = 0; k < n_out; ++k) {
+        const float time = len >= 2u ? (float)k / (float)(len - 1u) : 0.0f;
+        PsyBBox4 key;
+        for (int j = 0; j < 4; ++j) {
+            BBox6 b = b_empty();
+            if (j < cc) b = len >= 2u ? b_lerp_slice(bp[j], nk[j], time) : b_load(bp[j]);
+            key.v[0][j] = b.mn[0], key.v[1][j] = b.mx[0];
+            key.v[2][j] = b.mn[1], key.v[3][j] = b.mx[1];
+            key.v[4][j] = b.mn[2], key.v[5][j] = b.mx[2];
+        }
+        if (k == 0) nd.bounds = key;
+        if (len >= 2u) motion[(size_t)nd.key_base + k] = key;
+    }
+    nodes[idx4[i]] = nd;
+}
+
 }  // namespace psyd

@@ -1763,40 +1763,40 @@ int32_t psy_render_image_shard(PsyScene* sc, const PsyRenderParams* p, uint32_t 
 }
 
 // SURVEY.md N3 — LBVH topology of one mesh on the GPU (dbuild.cuh).  Host arrays in, host arrays out.
-int32_t psy_build_mesh_topology(PsyContext* ctx, const float* verts, uint32_t n_verts, uint32_t n_keys, const uint32_t* tri_idx,
-                                uint32_t n_tris, uint32_t tris_per_leaf, uint32_t* order, int32_t* left, int32_t* right,
-                                uint8_t* axis, uint32_t* n_internal, int32_t* root, uint32_t* depth) {
-    if (!ctx || !verts || !tri_idx || !order || !root || !depth || !n_internal || n_keys == 0 || tris_per_leaf == 0 ||
-        tris_per_leaf > 3)
-        return fail(PSY_ERR_INVALID, "psy_build_mesh_topology: bad argument");
-    if (n_tris == 0 || n_tris > (PSY_MAX_LEAF_START >> 2)) return fail(PSY_ERR_INVALID, "psy_build_mesh_topology: triangle count");
-    if (n_tris > tris_per_leaf && (!left || !right || !axis)) return fail(PSY_ERR_INVALID, "psy_build_mesh_topology: null output");
-    CK(cudaSetDevice(ctx->device));
+namespace {
+// The LBVH topology of one mesh, left on the device: sorted triangle order, and (when the mesh is more than one leaf)
+// the kept internal nodes' children / split axes, root = node 0.
+struct LbvhDevice {
+    DevBuf verts, idx, order, left, right, axis;
+    uint32_t n_internal = 0, depth = 0;
+    int32_t root = 0;
+};
+int32_t lbvh_device_topology(PsyContext* ctx, const float* verts, uint32_t n_verts, uint32_t n_keys, const uint32_t* tri_idx,
+                             uint32_t n_tris, uint32_t tris_per_leaf, LbvhDevice& L) {
     cudaStream_t st = ctx->stream;
-    DevBuf dverts, didx, dcent, dbox, dkeys, dkeys2, dvals, dvals2, dtmp, dleft, dright, daxis, drng, dnpar, dlpar, dkeep, dnew,
-        dleft2, dright2, daxis2, ddepth;
-    CK(dverts.upload(verts, (size_t)n_verts * n_keys * 3, st));
-    CK(didx.upload(tri_idx, (size_t)n_tris * 3, st));
+    DevBuf dcent, dbox, dkeys, dkeys2, dvals, dtmp, dleft, dright, daxis, drng, dnpar, dlpar, dkeep, dnew, ddepth;
+    CK(L.verts.upload(verts, (size_t)n_verts * n_keys * 3, st));
+    CK(L.idx.upload(tri_idx, (size_t)n_tris * 3, st));
     CK(dcent.alloc((size_t)n_tris * sizeof(float3)));
     const uint32_t box_init[6] = {~0u, ~0u, ~0u, 0u, 0u, 0u};
     CK(dbox.upload(box_init, 6, st));
     CK(dkeys.alloc((size_t)n_tris * 8));
     CK(dkeys2.alloc((size_t)n_tris * 8));
     CK(dvals.alloc((size_t)n_tris * 4));
-    CK(dvals2.alloc((size_t)n_tris * 4));
+    CK(L.order.alloc((size_t)n_tris * 4));
     const unsigned tb = (n_tris + 255) / 256;
-    k_lbvh_centroids<<<tb, 256, 0, st>>>(dverts.as<float>(), n_keys, didx.as<uint32_t>(), n_tris, dcent.as<float3>(),
+    k_lbvh_centroids<<<tb, 256, 0, st>>>(L.verts.as<float>(), n_keys, L.idx.as<uint32_t>(), n_tris, dcent.as<float3>(),
                                          dbox.as<uint32_t>());
     k_lbvh_morton<<<tb, 256, 0, st>>>(dcent.as<float3>(), n_tris, dbox.as<uint32_t>(), dkeys.as<uint64_t>(), dvals.as<uint32_t>());
     size_t tmp_bytes = 0, scan_bytes = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dkeys.as<uint64_t>(), dkeys2.as<uint64_t>(), dvals.as<uint32_t>(),
-                                       dvals2.as<uint32_t>(), (int)n_tris, 0, 63, st));
+                                       L.order.as<uint32_t>(), (int)n_tris, 0, 63, st));
     CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_tris, st));
     CK(dtmp.alloc(std::max(tmp_bytes, scan_bytes)));
     CK(cub::DeviceRadixSort::SortPairs(dtmp.p, tmp_bytes, dkeys.as<uint64_t>(), dkeys2.as<uint64_t>(), dvals.as<uint32_t>(),
-                                       dvals2.as<uint32_t>(), (int)n_tris, 0, 63, st));
-    *depth = 0;
-    *n_internal = 0;
+                                       L.order.as<uint32_t>(), (int)n_tris, 0, 63, st));
+    L.depth = 0;
+    L.n_internal = 0;
     if (n_tris > tris_per_leaf) {
         const int n_nodes = (int)n_tris - 1;  // of the radix tree over single triangles
         CK(dleft.alloc((size_t)n_nodes * 4));
@@ -1807,9 +1807,9 @@ int32_t psy_build_mesh_topology(PsyContext* ctx, const float* verts, uint32_t n_
         CK(dlpar.alloc((size_t)n_tris * 4));
         CK(dkeep.alloc((size_t)n_nodes * 4));
         CK(dnew.alloc((size_t)n_nodes * 4));
-        CK(dleft2.alloc((size_t)n_nodes * 4));
-        CK(dright2.alloc((size_t)n_nodes * 4));
-        CK(daxis2.alloc((size_t)n_nodes));
+        CK(L.left.alloc((size_t)n_nodes * 4));
+        CK(L.right.alloc((size_t)n_nodes * 4));
+        CK(L.axis.alloc((size_t)n_nodes));
         CK(ddepth.alloc(4));
         CK(cudaMemsetAsync(ddepth.p, 0, 4, st));
         const unsigned nb = ((unsigned)n_nodes + 255) / 256;
@@ -1818,28 +1818,151 @@ int32_t psy_build_mesh_topology(PsyContext* ctx, const float* verts, uint32_t n_
         k_lbvh_flag<<<nb, 256, 0, st>>>(drng.as<int2>(), n_nodes, (int)tris_per_leaf, dkeep.as<uint32_t>());
         CK(cub::DeviceScan::ExclusiveSum(dtmp.p, scan_bytes, dkeep.as<uint32_t>(), dnew.as<uint32_t>(), n_nodes, st));
         k_lbvh_emit<<<nb, 256, 0, st>>>(dleft.as<int32_t>(), dright.as<int32_t>(), daxis.as<uint8_t>(), drng.as<int2>(),
-                                        dkeep.as<uint32_t>(), dnew.as<uint32_t>(), n_nodes, dleft2.as<int32_t>(),
-                                        dright2.as<int32_t>(), daxis2.as<uint8_t>());
+                                        dkeep.as<uint32_t>(), dnew.as<uint32_t>(), n_nodes, L.left.as<int32_t>(),
+                                        L.right.as<int32_t>(), L.axis.as<uint8_t>());
         k_lbvh_depth<<<tb, 256, 0, st>>>(dnpar.as<int32_t>(), dlpar.as<int32_t>(), dkeep.as<uint32_t>(), (int)n_tris,
                                          ddepth.as<uint32_t>());
         CK(cudaGetLastError());
         uint32_t last_keep = 0, last_new = 0;
         CK(cudaMemcpyAsync(&last_keep, dkeep.as<uint32_t>() + (n_nodes - 1), 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&last_new, dnew.as<uint32_t>() + (n_nodes - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(depth, ddepth.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&L.depth, ddepth.p, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        const uint32_t n_int = last_keep + last_new;  // (the root spans everything: it is kept, and is new node 0)
-        *n_internal = n_int;
-        CK(cudaMemcpyAsync(left, dleft2.p, (size_t)n_int * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(right, dright2.p, (size_t)n_int * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(axis, daxis2.p, (size_t)n_int, cudaMemcpyDeviceToHost, st));
-        *root = 0;
+        L.n_internal = last_keep + last_new;  // (the root spans everything: it is kept, and is new node 0)
+        L.root = 0;
     } else {
-        *root = ~(int32_t)((0u << 2) | n_tris);  // the whole mesh is one leaf
+        L.root = ~(int32_t)((0u << 2) | n_tris);  // the whole mesh is one leaf
+        CK(cudaStreamSynchronize(st));
     }
-    CK(cudaMemcpyAsync(order, dvals2.p, (size_t)n_tris * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaGetLastError());
+    return PSY_OK;
+}
+}  // namespace
+
+int32_t psy_build_mesh_topology(PsyContext* ctx, const float* verts, uint32_t n_verts, uint32_t n_keys, const uint32_t* tri_idx,
+                                uint32_t n_tris, uint32_t tris_per_leaf, uint32_t* order, int32_t* left, int32_t* right,
+                                uint8_t* axis, uint32_t* n_internal, int32_t* root, uint32_t* depth) {
+    if (!ctx || !verts || !tri_idx || !order || !root || !depth || !n_internal || n_keys == 0 || tris_per_leaf == 0 ||
+        tris_per_leaf > 3)
+        return fail(PSY_ERR_INVALID, "psy_build_mesh_topology: bad argument");
+    if (n_tris == 0 || n_tris > (PSY_MAX_LEAF_START >> 2)) return fail(PSY_ERR_INVALID, "psy_build_mesh_topology: triangle count");
+    if (n_tris > tris_per_leaf && (!left || !right || !axis)) return fail(PSY_ERR_INVALID, "psy_build_mesh_topology: null output");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    LbvhDevice L;
+    const int32_t rc = lbvh_device_topology(ctx, verts, n_verts, n_keys, tri_idx, n_tris, tris_per_leaf, L);
+    if (rc != PSY_OK) return rc;
+    *depth = L.depth, *n_internal = L.n_internal, *root = L.root;
+    if (L.n_internal) {
+        CK(cudaMemcpyAsync(left, L.left.p, (size_t)L.n_internal * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(right, L.right.p, (size_t)L.n_internal * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(axis, L.axis.p, (size_t)L.n_internal, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(order, L.order.p, (size_t)n_tris * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    return PSY_OK;
+}
+
+// The whole mesh BVH on the device: LBVH topology, then bounds, union rule and BVH4 collapse (dbuild.cuh), left there
+// until psy_mesh_bvh_take copies it into the caller's arrays.
+struct PsyMeshBvh {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t n_tris = 0;
+    DevBuf order, nodes, motion;
+    PsyMeshBvhInfo info{};
+    float root_bounds[BUILD_MAX_KEYS * 6];
+};
+
+int32_t psy_mesh_bvh_build(PsyContext* ctx, const float* verts, uint32_t n_verts, uint32_t n_keys, const uint32_t* tri_idx,
+                           uint32_t n_tris, uint32_t tris_per_leaf, uint32_t obj_base, PsyMeshBvh** out, PsyMeshBvhInfo* info) {
+    if (!ctx || !verts || !tri_idx || !out || !info || n_keys == 0 || tris_per_leaf == 0 || tris_per_leaf > 3)
+        return fail(PSY_ERR_INVALID, "psy_mesh_bvh_build: bad argument");
+    if (n_keys > (uint32_t)BUILD_MAX_KEYS) return fail(PSY_ERR_INVALID, "psy_mesh_bvh_build: more time samples than the device build handles");
+    if (n_tris <= tris_per_leaf) return fail(PSY_ERR_INVALID, "psy_mesh_bvh_build: a mesh of one leaf has no nodes to build");
+    if ((uint64_t)obj_base + n_tris > PSY_MAX_LEAF_START || n_tris > (PSY_MAX_LEAF_START >> 2))
+        return fail(PSY_ERR_INVALID, "psy_mesh_bvh_build: triangle count");
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    LbvhDevice L;
+    int32_t rc = lbvh_device_topology(ctx, verts, n_verts, n_keys, tri_idx, n_tris, tris_per_leaf, L);
+    if (rc != PSY_OK) return rc;
+    const int n_int = (int)L.n_internal;
+    if (n_int <= 0) return fail(PSY_ERR_INVALID, "psy_mesh_bvh_build: empty topology");
+    std::unique_ptr<PsyMeshBvh> h(new PsyMeshBvh());
+    h->device = ctx->device, h->stream = st, h->n_tris = n_tris;
+    DevBuf parent, cb, cnk, ready, rootb, rootnk, is4, idx4, mcount, kbase, tmp;
+    CK(parent.alloc((size_t)n_int * 4));
+    CK(cb.alloc((size_t)n_int * 2 * n_keys * 6 * sizeof(float)));
+    CK(cnk.alloc((size_t)n_int * 2));
+    CK(ready.alloc((size_t)n_int * 4));
+    CK(rootb.alloc(sizeof(float) * BUILD_MAX_KEYS * 6));
+    CK(rootnk.alloc(4));
+    CK(is4.alloc((size_t)n_int * 4));
+    CK(idx4.alloc((size_t)n_int * 4));
+    CK(mcount.alloc((size_t)n_int * 4));
+    CK(kbase.alloc((size_t)n_int * 4));
+    CK(cudaMemsetAsync(ready.p, 0, (size_t)n_int * 4, st));
+    CK(cudaMemsetAsync(rootnk.p, 0, 4, st));
+    const unsigned nb = ((unsigned)n_int + 255) / 256;
+    k_b2_parents<<<nb, 256, 0, st>>>(L.left.as<int32_t>(), L.right.as<int32_t>(), n_int, parent.as<int32_t>());
+    k_b2_refit<<<((unsigned)(2 * n_int) + 127) / 128, 128, 0, st>>>(
+        L.verts.as<float>(), n_keys, L.idx.as<uint32_t>(), L.order.as<uint32_t>(), L.left.as<int32_t>(), L.right.as<int32_t>(),
+        parent.as<int32_t>(), n_int, cb.as<float>(), cnk.as<uint8_t>(), ready.as<uint32_t>(), rootb.as<float>(),
+        rootnk.as<uint32_t>());
+    k_b4_mark<<<nb, 256, 0, st>>>(L.left.as<int32_t>(), L.right.as<int32_t>(), parent.as<int32_t>(), cnk.as<uint8_t>(), n_int,
+                                  is4.as<uint32_t>(), mcount.as<uint32_t>());
+    size_t scan_bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, n_int, st));
+    CK(tmp.alloc(scan_bytes));
+    CK(cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, is4.as<uint32_t>(), idx4.as<uint32_t>(), n_int, st));
+    CK(cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, mcount.as<uint32_t>(), kbase.as<uint32_t>(), n_int, st));
+    uint32_t last[4] = {0, 0, 0, 0}, root_nk = 0;
+    CK(cudaMemcpyAsync(&last[0], is4.as<uint32_t>() + (n_int - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&last[1], idx4.as<uint32_t>() + (n_int - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&last[2], mcount.as<uint32_t>() + (n_int - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&last[3], kbase.as<uint32_t>() + (n_int - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&root_nk, rootnk.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->root_bounds, rootb.p, sizeof(h->root_bounds), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    const uint32_t n4 = last[0] + last[1], nm = last[2] + last[3];
+    if (root_nk == 0 || n4 == 0) return fail(PSY_ERR_CUDA, "psy_mesh_bvh_build: the refit did not reach the root");
+    CK(h->nodes.alloc((size_t)n4 * sizeof(PsyBvh4Node)));
+    CK(h->motion.alloc(std::max<size_t>((size_t)nm, 1) * sizeof(PsyBBox4)));
+    k_b4_emit<<<((unsigned)n_int + 127) / 128, 128, 0, st>>>(
+        L.left.as<int32_t>(), L.right.as<int32_t>(), L.axis.as<uint8_t>(), cb.as<float>(), cnk.as<uint8_t>(), is4.as<uint32_t>(),
+        idx4.as<uint32_t>(), kbase.as<uint32_t>(), n_int, n_keys, obj_base, h->nodes.as<PsyBvh4Node>(), h->motion.as<PsyBBox4>());
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    h->order = std::move(L.order);
+    h->info.n_nodes = n4;
+    h->info.n_motion = nm;
+    h->info.n_root_bounds = root_nk;
+    h->info.root = 0;                      // the binary root is at depth 0: BVH4 node 0
+    h->info.depth = L.depth / 2 + 1;       // like BVH4::construct_from_base (bvh4.rs:186-200)
+    h->info.binary_depth = L.depth;
+    *info = h->info;
+    *out = h.release();
+    return PSY_OK;
+}
+
+int32_t psy_mesh_bvh_take(PsyMeshBvh* h, uint32_t* order, PsyBvh4Node* nodes, PsyBBox4* motion, PsyBBox* root_bounds) {
+    if (!h) return PSY_OK;
+    std::unique_ptr<PsyMeshBvh> own(h);
+    if (!order && !nodes && !motion && !root_bounds) return PSY_OK;  // just dropped
+    if (!order || !nodes || !root_bounds || (h->info.n_motion && !motion)) return fail(PSY_ERR_INVALID, "psy_mesh_bvh_take: null output");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(order, h->order.p, (size_t)h->n_tris * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(nodes, h->nodes.p, (size_t)h->info.n_nodes * sizeof(PsyBvh4Node), cudaMemcpyDeviceToHost, st));
+    if (h->info.n_motion)
+        CK(cudaMemcpyAsync(motion, h->motion.p, (size_t)h->info.n_motion * sizeof(PsyBBox4), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (uint32_t k = 0; k < h->info.n_root_bounds; ++k)
+        for (int d = 0; d < 3; ++d) root_bounds[k].min[d] = h->root_bounds[6 * k + d], root_bounds[k].max[d] = h->root_bounds[6 * k + 3 + d];
     return PSY_OK;
 }
 

@@ -24,7 +24,16 @@ void* g_topo_ctx = nullptr;
 uint32_t g_topo_min_tris = 0;
 double g_topo_seconds = 0.0;
 uint32_t g_topo_meshes = 0;
+MeshBvhBuildFn g_bvh_build = nullptr;
+MeshBvhTakeFn g_bvh_take = nullptr;
+void* g_bvh_ctx = nullptr;
+uint32_t g_bvh_min_tris = 0;
 }  // namespace
+
+void set_mesh_bvh_builder(MeshBvhBuildFn build, MeshBvhTakeFn take, void* ctx, uint32_t min_tris) {
+    std::lock_guard<std::mutex> g(g_topo_mu);
+    g_bvh_build = build, g_bvh_take = take, g_bvh_ctx = ctx, g_bvh_min_tris = min_tris;
+}
 
 void set_mesh_topology_builder(MeshTopologyFn fn, void* ctx, uint32_t min_tris) {
     std::lock_guard<std::mutex> g(g_topo_mu);
@@ -172,51 +181,31 @@ struct Flattener {
         pm.vert_count = (uint32_t)vc;
         pm.vert_base = (uint32_t)(fs.verts.size() / 3);
         pm.has_normals = m.normals.empty() ? 0u : 1u;
-        fs.verts.reserve(fs.verts.size() + vc * k * 3);
-        for (size_t vi = 0; vi < vc; ++vi)
-            for (size_t ti = 0; ti < k; ++ti) {
-                const V3& p = m.verts[ti][vi];
-                fs.verts.push_back(p.x);
-                fs.verts.push_back(p.y);
-                fs.verts.push_back(p.z);
-            }
-        fs.normals.resize(fs.verts.size(), 0.0f);
-        if (pm.has_normals) {
-            size_t o = (size_t)pm.vert_base * 3;
-            for (size_t vi = 0; vi < vc; ++vi)
-                for (size_t ti = 0; ti < k; ++ti) {
-                    const V3& p = m.normals[ti][vi];
-                    fs.normals[o++] = p.x;
-                    fs.normals[o++] = p.y;
-                    fs.normals[o++] = p.z;
-                }
+        {
+            // the time keys of a vertex contiguous (PsySceneDesc.verts)
+            const size_t o0 = (size_t)pm.vert_base * 3;
+            fs.verts.resize(o0 + vc * k * 3);
+            fs.normals.resize(fs.verts.size(), 0.0f);
+            parallel_for(vc, 65536, [&](size_t b0, size_t e0) {
+                for (size_t vi = b0; vi < e0; ++vi)
+                    for (size_t ti = 0; ti < k; ++ti) {
+                        float* o = fs.verts.data() + o0 + (vi * k + ti) * 3;
+                        const V3& p = m.verts[ti][vi];
+                        o[0] = p.x, o[1] = p.y, o[2] = p.z;
+                        if (pm.has_normals) {
+                            float* q = fs.normals.data() + o0 + (vi * k + ti) * 3;
+                            const V3& nn = m.normals[ti][vi];
+                            q[0] = nn.x, q[1] = nn.y, q[2] = nn.z;
+                        }
+                    }
+            });
         }
         const bool timing = getenv("PSY_BUILD_TIMING") != nullptr && nt > 100000;
         auto tm0 = std::chrono::steady_clock::now();
-        // per-triangle bounds for every time sample (triangle_mesh.rs:86-99)
-        std::vector<BBox> bounds(nt * k);
-        std::vector<uint32_t> begin(nt + 1);
         for (size_t i = 0; i < nt; ++i) {
             auto& t = m.tris[i];
             if (t[0] >= vc || t[1] >= vc || t[2] >= vc) throw std::runtime_error("triangle index out of range");
         }
-        parallel_for(nt, 65536, [&](size_t b0, size_t e0) {
-            for (size_t i = b0; i < e0; ++i) {
-                begin[i] = (uint32_t)(i * k);
-                auto& t = m.tris[i];
-                for (size_t ti = 0; ti < k; ++ti) {
-                    V3 p0 = m.verts[ti][t[0]], p1 = m.verts[ti][t[1]], p2 = m.verts[ti][t[2]];
-                    BBox b;
-                    b.min = vmin(p0, vmin(p1, p2));
-                    b.max = vmax(p0, vmax(p1, p2));
-                    bounds[i * k + ti] = b;
-                }
-            }
-        });
-        begin[nt] = (uint32_t)(nt * k);
-        if (timing)
-            std::fprintf(stderr, "[build] mesh %zu triangles x %zu keys: triangle bounds %.3fs\n", nt, k,
-                         std::chrono::duration<double>(std::chrono::steady_clock::now() - tm0).count());
         std::vector<uint32_t> ids(nt);
         std::iota(ids.begin(), ids.end(), 0u);
         pm.tri_base = (uint32_t)(fs.tris.size() / 4);
@@ -225,6 +214,78 @@ struct Flattener {
         Bvh4Flat bvh;
         bool built = false;
         {
+            // the whole BVH4 of the mesh from the registered external (GPU) builder
+            MeshBvhBuildFn fb;
+            MeshBvhTakeFn ft;
+            void* fctx;
+            uint32_t fmin;
+            {
+                std::lock_guard<std::mutex> g(g_topo_mu);
+                fb = g_bvh_build, ft = g_bvh_take, fctx = g_bvh_ctx, fmin = g_bvh_min_tris;
+            }
+            if (fb && ft && nt >= fmin && nt > 3) {
+                auto t0 = std::chrono::steady_clock::now();
+                PsyMeshBvh* h = nullptr;
+                PsyMeshBvhInfo info{};
+                int32_t rc = fb(fctx, fs.verts.data() + (size_t)pm.vert_base * 3, (uint32_t)vc, (uint32_t)k, &m.tris[0][0],
+                                (uint32_t)nt, 3, pm.tri_base, &h, &info);
+                if (rc == 0 && info.binary_depth <= BVH_MAX_DEPTH) {
+                    bvh.nodes.resize(info.n_nodes);
+                    bvh.motion.resize(info.n_motion);
+                    std::vector<PsyBBox> rb(info.n_root_bounds);
+                    rc = ft(h, ids.data(), bvh.nodes.data(), bvh.motion.data(), rb.data());
+                    if (rc == 0) {
+                        bvh.root = info.root;
+                        bvh.depth = info.depth;
+                        for (auto& b : rb) {
+                            BBox x;
+                            x.min = v3(b.min[0], b.min[1], b.min[2]);
+                            x.max = v3(b.max[0], b.max[1], b.max[2]);
+                            bvh.bounds.push_back(x);
+                        }
+                        built = true;
+                        std::lock_guard<std::mutex> g(g_topo_mu);
+                        g_topo_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                        g_topo_meshes += 1;
+                    }
+                } else if (rc == 0) {
+                    ft(h, nullptr, nullptr, nullptr, nullptr);  // deeper than the reference allows: dropped
+                }
+                if (!built) {
+                    bvh = Bvh4Flat();
+                    std::iota(ids.begin(), ids.end(), 0u);
+                }
+                if (timing && built)
+                    std::fprintf(stderr, "[build] mesh %zu triangles x %zu keys: BVH4 from the device builder %.3fs\n", nt, k,
+                                 std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+            }
+        }
+        // per-triangle bounds for every time sample (triangle_mesh.rs:86-99)
+        std::vector<BBox> bounds;
+        std::vector<uint32_t> begin;
+        if (!built) {
+            tm0 = std::chrono::steady_clock::now();
+            bounds.resize(nt * k);
+            begin.resize(nt + 1);
+            parallel_for(nt, 65536, [&](size_t b0, size_t e0) {
+                for (size_t i = b0; i < e0; ++i) {
+                    begin[i] = (uint32_t)(i * k);
+                    auto& t = m.tris[i];
+                    for (size_t ti = 0; ti < k; ++ti) {
+                        V3 p0 = m.verts[ti][t[0]], p1 = m.verts[ti][t[1]], p2 = m.verts[ti][t[2]];
+                        BBox b;
+                        b.min = vmin(p0, vmin(p1, p2));
+                        b.max = vmax(p0, vmax(p1, p2));
+                        bounds[i * k + ti] = b;
+                    }
+                }
+            });
+            begin[nt] = (uint32_t)(nt * k);
+            if (timing)
+                std::fprintf(stderr, "[build] mesh %zu triangles x %zu keys: triangle bounds %.3fs\n", nt, k,
+                             std::chrono::duration<double>(std::chrono::steady_clock::now() - tm0).count());
+        }
+        if (!built) {
             // triangle order + binary topology from the registered external (GPU LBVH) builder
             MeshTopologyFn fn;
             void* fctx;

@@ -91,6 +91,11 @@ void psyh_set_mesh_topology_builder(void* fn, void* ctx, uint32_t min_tris) {
     set_mesh_topology_builder(reinterpret_cast<MeshTopologyFn>(fn), ctx, min_tris);
 }
 double psyh_take_mesh_topology_seconds(uint32_t* meshes_built) { return take_mesh_topology_seconds(meshes_built); }
+// ... and of whole mesh BVH4s (psy_mesh_bvh_build / psy_mesh_bvh_take); NULLs unregister.  Tried before the topology
+// builder; its time and mesh count are reported by psyh_take_mesh_topology_seconds as well.
+void psyh_set_mesh_bvh_builder(void* build, void* take, void* ctx, uint32_t min_tris) {
+    set_mesh_bvh_builder(reinterpret_cast<MeshBvhBuildFn>(build), reinterpret_cast<MeshBvhTakeFn>(take), ctx, min_tris);
+}
 
 const PsySceneDesc* psyh_scene_desc(void* scene) { return &static_cast<HostScene*>(scene)->flat->desc; }
 double psyh_build_seconds(void* scene) { return static_cast<HostScene*>(scene)->flat->build_seconds; }

@@ -32,6 +32,7 @@ int psyh_write_png(const char* path, const float* xyz, uint32_t w, uint32_t h);
 int psyh_write_exr(const char* path, const float* xyz, uint32_t w, uint32_t h);
 size_t psyh_bucket_base64(const float* xyz, uint32_t w, uint32_t h, char* out, size_t cap);
 void psyh_set_mesh_topology_builder(void* fn, void* ctx, uint32_t min_tris);
+void psyh_set_mesh_bvh_builder(void* build, void* take, void* ctx, uint32_t min_tris);
 int psyh_synth_displaced_grid(uint32_t quads_per_side, uint32_t n_vert_keys, uint32_t n_xform_keys, uint32_t res_x,
                               uint32_t res_y, uint32_t spp, uint32_t seed, void** out);
 int psyh_synth_instanced(uint32_t asset_quads, uint32_t n_assets, uint32_t n_clusters, uint32_t inst_per_cluster,
@@ -203,7 +204,12 @@ int main(int argc, char** argv) {
     PsyContext* ctx = nullptr;
     if (devices.empty()) devices.push_back(device);
     if (psy_init(devices.data(), (int)devices.size(), &ctx) != PSY_OK) die(std::string("psy_init: ") + psy_last_error());
-    if (gpu_build) psyh_set_mesh_topology_builder(reinterpret_cast<void*>(&psy_build_mesh_topology), ctx, 1u << 16);
+    if (gpu_build) {
+        // whole mesh BVH4s on the device; meshes it refuses (more than 8 time keys) get at least their topology there
+        psyh_set_mesh_bvh_builder(reinterpret_cast<void*>(&psy_mesh_bvh_build), reinterpret_cast<void*>(&psy_mesh_bvh_take), ctx,
+                                  1u << 16);
+        psyh_set_mesh_topology_builder(reinterpret_cast<void*>(&psy_build_mesh_topology), ctx, 1u << 16);
+    }
     std::string device_names;
     for (size_t k = 0; k < devices.size(); ++k) device_names += (k ? "," : "") + std::to_string(devices[k]);
 

@@ -1,6 +1,10 @@
-"""mesh BVHs whose triangle order and topology come from the GPU LBVH build (psy_build_mesh_topology,
-dbuild.cuh).  The tree differs from the host's SAH tree, the hits must not: the CUDA path and the oracle traverse the
-SAME GPU-built tree bit for bit, and both find the closest hits of the SAH-built scene."""
+"""mesh BVHs built on the GPU (dbuild.cuh) — the whole BVH4 (psy_mesh_bvh_build: LBVH topology, bounds,
+union rule, collapse) or only triangle order and topology (psy_build_mesh_topology, the host doing the rest).  The tree
+differs from the host's SAH tree, the hits must not: the CUDA path and the oracle traverse the SAME GPU-built tree bit
+for bit, and both find the closest hits of the SAH-built scene.  And the two GPU modes must agree with each other:
+same topology, same arithmetic, hence the same nodes bit for bit, in another order."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -12,9 +16,9 @@ from test_host_and_abi import check_bvh
 pytestmark = pytest.mark.gpu
 
 
-def build_pair(make):
+def build_pair(make, mode="bvh4"):
     sah = make()
-    api.enable_gpu_build(min_tris=64)
+    api.enable_gpu_build(min_tris=64, mode=mode)
     try:
         gpu = make()
     finally:
@@ -29,8 +33,9 @@ def build_pair(make):
     lambda: api.Scene.synth_instanced(asset_quads=80, n_assets=3, n_clusters=9, inst_per_cluster=5, lights_per_cluster=4,
                                       cluster_xform_keys=2, res=(96, 54), spp=4, seed=4, motion_pct=1250),
 ])
-def test_gpu_built_tree_is_valid_and_gives_the_same_hits(make):
-    sah, gpu = build_pair(make)
+@pytest.mark.parametrize("mode", ["bvh4", "topology"])
+def test_gpu_built_tree_is_valid_and_gives_the_same_hits(make, mode):
+    sah, gpu = build_pair(make, mode)
     d = gpu.desc.contents
     for m in range(d.n_meshes):
         mesh = d.meshes[m]
@@ -55,3 +60,75 @@ def test_gpu_built_tree_is_valid_and_gives_the_same_hits(make):
     b, _ = api.Renderer(gpu).render()
     rel = np.linalg.norm(a - b) / np.linalg.norm(a)
     assert rel < 2e-3, rel
+
+
+def node_bits(d, ref):
+    """Everything of a BVH4 node but its child references, as bytes: code, counts, bounds and motion keys."""
+    n = d.nodes[ref]
+    out = [bytes(C.string_at(C.addressof(n.bounds), C.sizeof(n.bounds))),
+           (n.traversal_code, n.n_keys, n.n_children).__repr__().encode()]
+    if n.n_keys > 1:
+        for k in range(n.n_keys):
+            kb = d.motion_bounds[n.key_base + k]
+            out.append(bytes(C.string_at(C.addressof(kb), C.sizeof(kb))))
+    return b"".join(out)
+
+
+def same_tree(da, root_a, db, root_b):
+    """Walks two BVH4s in step: equal node contents, equal leaves, whatever the node numbering."""
+    stack = [(root_a, root_b)]
+    nodes = 0
+    while stack:
+        a, b = stack.pop()
+        leaf_a, leaf_b = bool(a & 0x80000000), bool(b & 0x80000000)
+        assert leaf_a == leaf_b
+        if leaf_a:
+            assert a == b
+            continue
+        assert node_bits(da, a) == node_bits(db, b), f"node {a} / {b}"
+        nodes += 1
+        na, nb = da.nodes[a], db.nodes[b]
+        for c in range(4):
+            if c < na.n_children:
+                stack.append((na.child[c], nb.child[c]))
+            else:
+                assert na.child[c] == nb.child[c] == abi.PSY_NONE
+    return nodes
+
+
+@pytest.mark.parametrize("make", [
+    # 4 vertex keys: nodes with one key and with four, the union rule deciding at every level
+    lambda: api.Scene.synth_displaced_grid(120, n_vert_keys=4, n_xform_keys=2, res=(64, 36), spp=1, seed=3),
+    lambda: api.Scene.synth_displaced_grid(90, n_vert_keys=1, n_xform_keys=1, res=(64, 36), spp=1, seed=9),
+    lambda: api.Scene.synth_displaced_grid(70, n_vert_keys=3, n_xform_keys=1, res=(64, 36), spp=1, seed=5),
+    lambda: api.Scene.synth_instanced(asset_quads=60, n_assets=4, n_clusters=4, inst_per_cluster=3, lights_per_cluster=2,
+                                      cluster_xform_keys=2, res=(64, 36), spp=1, seed=4),
+])
+def test_device_built_bvh4_is_the_hosts_bvh4_of_the_same_topology(make):
+    scenes = {}
+    for mode in ("bvh4", "topology"):
+        api.enable_gpu_build(min_tris=64, mode=mode)
+        try:
+            scenes[mode] = make()
+        finally:
+            api.disable_gpu_build()
+        assert api.gpu_build_seconds()[1] >= 1
+    da, db = scenes["bvh4"].desc.contents, scenes["topology"].desc.contents
+    assert da.n_meshes == db.n_meshes and da.n_nodes == db.n_nodes and da.n_motion_bounds == db.n_motion_bounds
+    assert da.n_tris == db.n_tris
+    ta = np.ctypeslib.as_array(da.tris, shape=(da.n_tris * 4,))
+    tb = np.ctypeslib.as_array(db.tris, shape=(db.n_tris * 4,))
+    assert np.array_equal(ta, tb)  # the same triangle order
+    multi_key = walked = 0
+    for m in range(da.n_meshes):
+        ma, mb = da.meshes[m], db.meshes[m]
+        assert (ma.tri_base, ma.tri_count, ma.bvh_depth, ma.bounds_count) == (mb.tri_base, mb.tri_count, mb.bvh_depth,
+                                                                             mb.bounds_count)
+        for k in range(ma.bounds_count):
+            ba, bb = da.obj_bounds[ma.bounds_base + k], db.obj_bounds[mb.bounds_base + k]
+            assert bytes(C.string_at(C.addressof(ba), C.sizeof(ba))) == bytes(C.string_at(C.addressof(bb), C.sizeof(bb)))
+        walked += same_tree(da, ma.root, db, mb.root)  # (0 for a mesh that is one leaf, like the ground plane)
+        multi_key += sum(1 for j in range(da.n_nodes) if da.nodes[j].n_keys > 1) if m == 0 else 0
+    assert walked > 100
+    if da.meshes[0].n_keys > 1:
+        assert multi_key > 0  # the motion-key path of the device build is exercised
