@@ -132,3 +132,38 @@ def test_device_built_bvh4_is_the_hosts_bvh4_of_the_same_topology(make):
     assert walked > 100
     if da.meshes[0].n_keys > 1:
         assert multi_key > 0  # the motion-key path of the device build is exercised
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_scenes_build_the_same_on_device_and_host_and_hit_the_same(seed):
+    """The fuzz scenes' small meshes (boxes, fans, ragged patches of quads and triangles, 1-3 time keys): Morton ties,
+    leaves of one, two and three triangles at every depth, subtrees that end at odd and even depth."""
+    from scenes import random_scene_text
+    text = random_scene_text(seed)
+    scenes = {"sah": api.Scene.from_psy_string(text)}
+    for mode in ("bvh4", "topology"):
+        api.enable_gpu_build(min_tris=4, mode=mode)
+        try:
+            scenes[mode] = api.Scene.from_psy_string(text)
+        finally:
+            api.disable_gpu_build()
+        assert api.gpu_build_seconds()[1] >= 1
+    da, db = scenes["bvh4"].desc.contents, scenes["topology"].desc.contents
+    assert (da.n_meshes, da.n_nodes, da.n_motion_bounds, da.n_tris) == (db.n_meshes, db.n_nodes, db.n_motion_bounds, db.n_tris)
+    assert np.array_equal(np.ctypeslib.as_array(da.tris, shape=(da.n_tris * 4,)),
+                          np.ctypeslib.as_array(db.tris, shape=(db.n_tris * 4,)))
+    for m in range(da.n_meshes):
+        ma, mb = da.meshes[m], db.meshes[m]
+        assert (ma.bvh_depth, ma.bounds_count) == (mb.bvh_depth, mb.bounds_count)
+        same_tree(da, ma.root, db, mb.root)
+        check_bvh(da, ma.root, True, ma.tri_base, ma.tri_count)
+    rays = probe_rays(scenes["bvh4"], n_random=6000, seed=500 + seed)
+    gh = api.Tracer(scenes["bvh4"]).trace(rays)
+    oh = O.trace_rays(da, rays)[0]
+    for k in ("kind", "prim_id", "inst_id", "path_id", "t", "b0", "b1", "b2"):
+        assert np.array_equal(gh[k], oh[k]), k
+    sh = O.trace_rays(scenes["sah"].desc, rays)[0]
+    closest = (rays["flags"] & 1) == 0
+    assert np.array_equal(oh["kind"][closest], sh["kind"][closest])
+    hit = closest & (oh["kind"] == abi.HIT_TRIANGLE)
+    assert np.array_equal(oh["t"][hit], sh["t"][hit])
