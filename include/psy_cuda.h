@@ -400,23 +400,27 @@ int32_t psy_build_mesh_topology(PsyContext* ctx, const float* verts, uint32_t n_
  * arithmetic as the host builder: given the same topology the nodes are the host's bit for bit, in another order
  * (tests/test_gpu_build.py).
  *   psy_mesh_bvh_build  inputs as psy_build_mesh_topology; `obj_base` is added to the leaves' triangle positions
- *                       (PsyMesh.tri_base).  The result stays on the device behind *out; *info says how much room the
+ *                       (PsyMesh.tri_base), `node_base` to the references of internal children and `key_base` to the
+ *                       key_base of nodes with time keys: where this mesh's nodes / keys will start in
+ *                       PsySceneDesc.nodes / .motion_bounds, so that psy_mesh_bvh_take can write them in place.
+ *                       The result stays on the device behind *out; *info says how much room the
  *                       caller's arrays need.  Meshes of <= tris_per_leaf triangles or more than 8 time keys are refused
  *                       (PSY_ERR_INVALID): the host builds those.
  *   psy_mesh_bvh_take   copies the result out and frees the handle (also on error; all-NULL arrays just free it):
- *                       order[n_tris]; nodes[n_nodes], child references and key_base local to this mesh (node 0 is
- *                       the root); motion[n_motion]; root_bounds[n_root_bounds]. */
+ *                       order[n_tris]; nodes[n_nodes] (the first is the root); motion[n_motion];
+ *                       root_bounds[n_root_bounds]. */
 typedef struct PsyMeshBvh PsyMeshBvh;
 typedef struct PsyMeshBvhInfo {
     uint32_t n_nodes;       /* BVH4 nodes */
     uint32_t n_motion;      /* PsyBBox4 keys of the nodes with n_keys > 1 */
     uint32_t n_root_bounds; /* keys of the whole mesh's bounds (1 or n_keys) */
-    uint32_t root;          /* child reference of the root, local (0) */
+    uint32_t root;          /* child reference of the root (= node_base) */
     uint32_t depth;         /* BVH4 depth as construct_from_base reports it: binary depth / 2 + 1 */
     uint32_t binary_depth;  /* depth of the deepest leaf of the binary tree (root = 0) */
 } PsyMeshBvhInfo;
 int32_t psy_mesh_bvh_build(PsyContext* ctx, const float* verts, uint32_t n_verts, uint32_t n_keys, const uint32_t* tri_idx,
-                           uint32_t n_tris, uint32_t tris_per_leaf, uint32_t obj_base, PsyMeshBvh** out, PsyMeshBvhInfo* info);
+                           uint32_t n_tris, uint32_t tris_per_leaf, uint32_t obj_base, uint32_t node_base, uint32_t key_base,
+                           PsyMeshBvh** out, PsyMeshBvhInfo* info);
 int32_t psy_mesh_bvh_take(PsyMeshBvh* bvh, uint32_t* order, PsyBvh4Node* nodes, PsyBBox4* motion, PsyBBox* root_bounds);
 
 /* Page-locks / releases caller memory (cudaHostRegister): scene arrays that are uploaded every frame, result images

@@ -377,7 +377,8 @@ __global__ void __launch_bounds__(128) k_b4_emit(const int32_t* __restrict__ lef
                                                  const uint8_t* __restrict__ axis, const float* __restrict__ cb,
                                                  const uint8_t* __restrict__ cnk, const uint32_t* __restrict__ is4,
                                                  const uint32_t* __restrict__ idx4, const uint32_t* __restrict__ kbase,
-                                                 int n_int, uint32_t n_keys, uint32_t obj_base, PsyBvh4Node* __restrict__ nodes,
+                                                 int n_int, uint32_t n_keys, uint32_t obj_base, uint32_t node_base,
+                                                 uint32_t key_base, PsyBvh4Node* __restrict__ nodes,
                                                  PsyBBox4* __restrict__ motion) {
     const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (i >= n_int || !is4[i]) return;
@@ -419,7 +420,8 @@ __global__ void __launch_bounds__(128) k_b4_emit(const int32_t* __restrict__ lef
     nd.traversal_code = code;
     nd.n_children = (uint32_t)cc;
     nd.n_keys = len;
-    nd.key_base = len >= 2u ? kbase[i] : 0u;
+    const uint32_t my_keys = len >= 2u ? kbase[i] : 0u;  // (local: where this node's keys go in `motion`)
+    nd.key_base = len >= 2u ? key_base + my_keys : 0u;
     for (int j = 0; j < 4; ++j) {
         if (j >= cc) {
             nd.child[j] = PSY_NONE;
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(128) k_b4_emit(const int32_t* __restrict__ lef
             const uint32_t lc = (uint32_t)~ref[j];
             nd.child[j] = PSY_CHILD_LEAF(obj_base + (lc >> 2), lc & 3u);
         } else {
-            nd.child[j] = idx4[ref[j]];
+            nd.child[j] = node_base + idx4[ref[j]];
         }
     }
     const uint32_t n_out = len >= 2u ? len : 1u;
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(128) k_b4_emit(const int32_t* __restrict__ lef
             key.v[4][j] = b.mn[2], key.v[5][j] = b.mx[2];
         }
         if (k == 0) nd.bounds = key;
-        if (len >= 2u) motion[(size_t)nd.key_base + k] = key;
+        if (len >= 2u) motion[(size_t)my_keys + k] = key;
     }
     nodes[idx4[i]] = nd;
 }

@@ -1876,12 +1876,14 @@ struct PsyMeshBvh {
 };
 
 int32_t psy_mesh_bvh_build(PsyContext* ctx, const float* verts, uint32_t n_verts, uint32_t n_keys, const uint32_t* tri_idx,
-                           uint32_t n_tris, uint32_t tris_per_leaf, uint32_t obj_base, PsyMeshBvh** out, PsyMeshBvhInfo* info) {
+                           uint32_t n_tris, uint32_t tris_per_leaf, uint32_t obj_base, uint32_t node_base, uint32_t key_base,
+                           PsyMeshBvh** out, PsyMeshBvhInfo* info) {
     if (!ctx || !verts || !tri_idx || !out || !info || n_keys == 0 || tris_per_leaf == 0 || tris_per_leaf > 3)
         return fail(PSY_ERR_INVALID, "psy_mesh_bvh_build: bad argument");
     if (n_keys > (uint32_t)BUILD_MAX_KEYS) return fail(PSY_ERR_INVALID, "psy_mesh_bvh_build: more time samples than the device build handles");
     if (n_tris <= tris_per_leaf) return fail(PSY_ERR_INVALID, "psy_mesh_bvh_build: a mesh of one leaf has no nodes to build");
-    if ((uint64_t)obj_base + n_tris > PSY_MAX_LEAF_START || n_tris > (PSY_MAX_LEAF_START >> 2))
+    if ((uint64_t)obj_base + n_tris > PSY_MAX_LEAF_START || n_tris > (PSY_MAX_LEAF_START >> 2) ||
+        (uint64_t)node_base + n_tris >= 0x7FFFFFFFull)
         return fail(PSY_ERR_INVALID, "psy_mesh_bvh_build: triangle count");
     *out = nullptr;
     CK(cudaSetDevice(ctx->device));
@@ -1934,14 +1936,15 @@ int32_t psy_mesh_bvh_build(PsyContext* ctx, const float* verts, uint32_t n_verts
     CK(h->motion.alloc(std::max<size_t>((size_t)nm, 1) * sizeof(PsyBBox4)));
     k_b4_emit<<<((unsigned)n_int + 127) / 128, 128, 0, st>>>(
         L.left.as<int32_t>(), L.right.as<int32_t>(), L.axis.as<uint8_t>(), cb.as<float>(), cnk.as<uint8_t>(), is4.as<uint32_t>(),
-        idx4.as<uint32_t>(), kbase.as<uint32_t>(), n_int, n_keys, obj_base, h->nodes.as<PsyBvh4Node>(), h->motion.as<PsyBBox4>());
+        idx4.as<uint32_t>(), kbase.as<uint32_t>(), n_int, n_keys, obj_base, node_base, key_base, h->nodes.as<PsyBvh4Node>(),
+        h->motion.as<PsyBBox4>());
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     h->order = std::move(L.order);
     h->info.n_nodes = n4;
     h->info.n_motion = nm;
     h->info.n_root_bounds = root_nk;
-    h->info.root = 0;                      // the binary root is at depth 0: BVH4 node 0
+    h->info.root = node_base;              // the binary root is at depth 0: this mesh's first BVH4 node
     h->info.depth = L.depth / 2 + 1;       // like BVH4::construct_from_base (bvh4.rs:186-200)
     h->info.binary_depth = L.depth;
     *info = h->info;

@@ -212,9 +212,10 @@ struct Flattener {
         pm.tri_count = (uint32_t)nt;
         if ((size_t)pm.tri_base + nt > PSY_MAX_LEAF_START) throw std::runtime_error("too many triangles");
         Bvh4Flat bvh;
-        bool built = false;
+        bool built = false, in_place = false;
         {
-            // the whole BVH4 of the mesh from the registered external (GPU) builder
+            // the whole BVH4 of the mesh from the registered external (GPU) builder, written straight
+            // into the scene's node / key arrays
             MeshBvhBuildFn fb;
             MeshBvhTakeFn ft;
             void* fctx;
@@ -227,14 +228,21 @@ struct Flattener {
                 auto t0 = std::chrono::steady_clock::now();
                 PsyMeshBvh* h = nullptr;
                 PsyMeshBvhInfo info{};
-                int32_t rc = fb(fctx, fs.verts.data() + (size_t)pm.vert_base * 3, (uint32_t)vc, (uint32_t)k, &m.tris[0][0],
-                                (uint32_t)nt, 3, pm.tri_base, &h, &info);
+                const size_t node_base = fs.nodes.size(), key_base = fs.motion_bounds.size();
+                int32_t rc = node_base + nt < 0x7FFFFFFFu
+                                 ? fb(fctx, fs.verts.data() + (size_t)pm.vert_base * 3, (uint32_t)vc, (uint32_t)k, &m.tris[0][0],
+                                      (uint32_t)nt, 3, pm.tri_base, (uint32_t)node_base, (uint32_t)key_base, &h, &info)
+                                 : -1;
                 if (rc == 0 && info.binary_depth <= BVH_MAX_DEPTH) {
-                    bvh.nodes.resize(info.n_nodes);
-                    bvh.motion.resize(info.n_motion);
+                    fs.nodes.resize(node_base + info.n_nodes);
+                    fs.motion_bounds.resize(key_base + info.n_motion);
                     std::vector<PsyBBox> rb(info.n_root_bounds);
-                    rc = ft(h, ids.data(), bvh.nodes.data(), bvh.motion.data(), rb.data());
-                    if (rc == 0) {
+                    rc = ft(h, ids.data(), fs.nodes.data() + node_base, fs.motion_bounds.data() + key_base, rb.data());
+                    if (rc != 0) {
+                        fs.nodes.resize(node_base);
+                        fs.motion_bounds.resize(key_base);
+                    } else {
+                        in_place = true;
                         bvh.root = info.root;
                         bvh.depth = info.depth;
                         for (auto& b : rb) {
@@ -327,7 +335,10 @@ struct Flattener {
                 o[0] = t[0], o[1] = t[2], o[2] = t[1], o[3] = ids[i];
             }
         });
-        append_bvh(bvh, pm.root);
+        if (in_place)
+            pm.root = bvh.root;
+        else
+            append_bvh(bvh, pm.root);
         pm.bvh_depth = bvh.depth;
         pm.bounds_base = (uint32_t)fs.obj_bounds.size();
         pm.bounds_count = (uint32_t)bvh.bounds.size();
