@@ -33,6 +33,7 @@ int psyh_write_exr(const char* path, const float* xyz, uint32_t w, uint32_t h);
 size_t psyh_bucket_base64(const float* xyz, uint32_t w, uint32_t h, char* out, size_t cap);
 void psyh_set_mesh_topology_builder(void* fn, void* ctx, uint32_t min_tris);
 void psyh_set_mesh_bvh_builder(void* build, void* take, void* ctx, uint32_t min_tris);
+double psyh_take_mesh_topology_seconds(uint32_t* meshes_built);
 int psyh_synth_displaced_grid(uint32_t quads_per_side, uint32_t n_vert_keys, uint32_t n_xform_keys, uint32_t res_x,
                               uint32_t res_y, uint32_t spp, uint32_t seed, void** out);
 int psyh_synth_instanced(uint32_t asset_quads, uint32_t n_assets, uint32_t n_clusters, uint32_t inst_per_cluster,
@@ -248,6 +249,11 @@ int main(int argc, char** argv) {
         PsyScene* scene = nullptr;
         if (psy_scene_create(ctx, desc, &scene) != PSY_OK) die(std::string("psy_scene_create: ") + psy_last_error());
         if (!serialized) std::printf("\tBuilt scene in %.3fs\n", t.tick());
+        if (gpu_build && !serialized) {
+            uint32_t meshes = 0;
+            const double secs = psyh_take_mesh_topology_seconds(&meshes);
+            std::printf("\t%u mesh BVHs built on the GPU in %.3fs\n", meshes, secs);
+        }
         if (!probe_in.empty()) {
             // --probe-rays FILE: trace a file of PsyRay records (36 bytes each: orig[3] dir[3] time max_t flags) through
             // the scene instead of rendering it, and write the PsyHit records (32 bytes each) to --probe-out (default

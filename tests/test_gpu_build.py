@@ -167,3 +167,26 @@ def test_random_scenes_build_the_same_on_device_and_host_and_hit_the_same(seed):
     assert np.array_equal(oh["kind"][closest], sh["kind"][closest])
     hit = closest & (oh["kind"] == abi.HIT_TRIANGLE)
     assert np.array_equal(oh["t"][hit], sh["t"][hit])
+
+
+def test_cli_gpu_build_flag(tmp_path):
+    """`psychopath --synth C3 --gpu-build`: BASELINE config 2's 10 M triangles with both mesh BVH4s from the device, and
+    the picture of the SAH-built scene (same samples, same closest hits; only exact ties may pick another triangle)."""
+    import os
+    import subprocess
+    import cv2
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(repo, "bin", "psychopath")
+    imgs = {}
+    for name, flags in (("sah", []), ("gpu", ["--gpu-build"])):
+        d = tmp_path / name
+        d.mkdir()
+        out = subprocess.run([exe, "--synth", "C3", "--spp", "2"] + flags, cwd=d, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr
+        if flags:
+            assert "2 mesh BVHs built on the GPU" in out.stdout, out.stdout
+        pngs = [f for f in os.listdir(d) if f.endswith(".png")]
+        assert len(pngs) == 1
+        imgs[name] = cv2.imread(str(d / pngs[0])).astype(np.int32)
+    assert imgs["sah"].shape == imgs["gpu"].shape == (1080, 1920, 3) and imgs["sah"].mean() > 2
+    assert (np.abs(imgs["sah"] - imgs["gpu"]).max(axis=-1) > 2).mean() < 1e-3
