@@ -190,6 +190,16 @@ def load_host():
     lib.psyh_bucket_list.restype = u32
     lib.psyh_set_mesh_topology_builder.argtypes = [C.c_void_p, C.c_void_p, u32]
     lib.psyh_set_mesh_topology_builder.restype = None
+    lib.psyh_test_datatree_dump.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+    lib.psyh_test_datatree_dump.restype = C.c_long
+    lib.psyh_test_parse_floats.argtypes = [C.c_char_p, C.POINTER(f32), C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.psyh_test_parse_floats.restype = C.c_size_t
+    lib.psyh_test_parse_uints.argtypes = [C.c_char_p, C.POINTER(u32), C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.psyh_test_parse_uints.restype = C.c_size_t
+    lib.psyh_test_quick_select.argtypes = [C.POINTER(C.c_int32), C.c_size_t, C.c_size_t]
+    lib.psyh_test_quick_select.restype = None
+    lib.psyh_test_log2_64.argtypes = [C.c_uint64]
+    lib.psyh_test_log2_64.restype = C.c_uint64
     lib.psyh_set_mesh_bvh_builder.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u32]
     lib.psyh_set_mesh_bvh_builder.restype = None
     lib.psyh_take_mesh_topology_seconds.argtypes = [C.POINTER(u32)]

@@ -1,12 +1,14 @@
 // host_api.cpp — C entry points of libpsy_host.so: the host side above the CUDA C ABI.
 // (The reference's host is Rust; no Rust toolchain exists in this image, so the host that parses,
 // builds acceleration structures and schedules buckets is restated in C++ — SURVEY.md F1.)
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
 
+#include "bvh_build.h"
 #include "scene_ir.h"
 
 using namespace psyh;
@@ -96,6 +98,29 @@ double psyh_take_mesh_topology_seconds(uint32_t* meshes_built) { return take_mes
 void psyh_set_mesh_bvh_builder(void* build, void* take, void* ctx, uint32_t min_tris) {
     set_mesh_bvh_builder(reinterpret_cast<MeshBvhBuildFn>(build), reinterpret_cast<MeshBvhTakeFn>(take), ctx, min_tris);
 }
+
+// ---- test hooks: the reference's own unit tests for the parser and the build helpers are restated against these
+// (tests/test_parse_semantics.py, tests/test_host_and_abi.py)
+long psyh_test_datatree_dump(const char* text, char* out, size_t cap) {
+    std::string r;
+    if (guarded([&]() { r = datatree_dump(text); }) != 0) return -1;
+    if (out && cap) {
+        const size_t n = std::min(cap - 1, r.size());
+        std::memcpy(out, r.data(), n);
+        out[n] = 0;
+    }
+    return (long)r.size();
+}
+size_t psyh_test_parse_floats(const char* text, float* out, size_t cap, size_t* rest) {
+    return test_parse_floats(text, out, cap, rest);
+}
+size_t psyh_test_parse_uints(const char* text, uint32_t* out, size_t cap, size_t* rest) {
+    return test_parse_uints(text, out, cap, rest);
+}
+void psyh_test_quick_select(int32_t* list, size_t len, size_t n) {
+    quick_select_ref(list, len, n, [](int32_t a, int32_t b) { return a < b; });
+}
+uint64_t psyh_test_log2_64(uint64_t n) { return log2_64(n); }
 
 const PsySceneDesc* psyh_scene_desc(void* scene) { return &static_cast<HostScene*>(scene)->flat->desc; }
 double psyh_build_seconds(void* scene) { return static_cast<HostScene*>(scene)->flat->build_seconds; }

@@ -119,30 +119,59 @@ std::string trim(const std::string& s) {
     return s.substr(a, b - a);
 }
 
-// Sequence of whitespace-separated floats; returns how many were read, stops at the first non-number.
-std::vector<float> parse_floats(const std::string& text) {
+// Sequence of whitespace-separated floats (basics.rs:16-18 ws_f32, repeated); stops at the first non-number.
+// `rest`: where it stopped (trailing whitespace consumed, like ws_f32's multispace0).
+std::vector<float> parse_floats(const std::string& text, size_t* rest = nullptr) {
     std::vector<float> out;
     const char* c = text.c_str();
     char* end = nullptr;
     for (;;) {
         while (*c && isspace((unsigned char)*c)) ++c;
         if (!*c) break;
-        float v = strtof(c, &end);
-        if (end == c) break;
-        out.push_back(v);
-        c = end;
+        // nom 5's recognize_float: [sign] (digits ['.' [digits]] | '.' digits) [('e'|'E') [sign] digits] — no hex, no
+        // "inf" / "nan"; the text it recognises goes to the correctly rounded conversion (Rust's f32::from_str / strtof)
+        const char* q = (*c == '-' || *c == '+') ? c + 1 : c;
+        const char* ds = q;
+        while (isdigit((unsigned char)*q)) ++q;
+        if (q > ds) {
+            if (*q == '.') {
+                ++q;
+                while (isdigit((unsigned char)*q)) ++q;
+            }
+        } else if (*q == '.' && isdigit((unsigned char)q[1])) {
+            ++q;
+            while (isdigit((unsigned char)*q)) ++q;
+        } else {
+            break;
+        }
+        if (*q == 'e' || *q == 'E') {
+            const char* e = q + 1;
+            if (*e == '+' || *e == '-') ++e;
+            if (isdigit((unsigned char)*e)) {
+                while (isdigit((unsigned char)*e)) ++e;
+                q = e;
+            }
+        }
+        const std::string tok(c, q);
+        out.push_back(strtof(tok.c_str(), &end));
+        c = q;
     }
+    if (rest) *rest = (size_t)(c - text.c_str());
     return out;
 }
 
+// Fields the reference reads with all_consuming(...) (psy.rs:277-407, psy_light.rs, psy_surface_shader.rs:80-96):
+// exactly `count` numbers and nothing else in the leaf.
 std::vector<float> parse_floats_exact(const Node& n, size_t count, const char* what) {
-    std::vector<float> v = parse_floats(n.contents);
-    if (v.size() != count)
+    size_t rest = 0;
+    std::vector<float> v = parse_floats(n.contents, &rest);
+    if (v.size() != count || rest != n.contents.size())
         throw std::runtime_error(std::string("psy parse error: ") + what + " at byte " + std::to_string(n.offset));
     return v;
 }
 
-std::vector<uint32_t> parse_uints(const std::string& text) {
+// ws_u32 / ws_usize (basics.rs:20-26), repeated: digits only
+std::vector<uint32_t> parse_uints(const std::string& text, size_t* rest = nullptr) {
     std::vector<uint32_t> out;
     const char* c = text.c_str();
     for (;;) {
@@ -153,15 +182,19 @@ std::vector<uint32_t> parse_uints(const std::string& text) {
         out.push_back((uint32_t)v);
         c = end;
     }
+    if (rest) *rest = (size_t)(c - text.c_str());
     return out;
+}
+std::vector<uint32_t> parse_uints_exact(const std::string& text, size_t count, const char* what) {
+    size_t rest = 0;
+    std::vector<uint32_t> v = parse_uints(text, &rest);
+    if (v.size() != count || rest != text.size()) throw std::runtime_error(what);
+    return v;
 }
 
 // parse_matrix (psy.rs:556-572): 16 numbers, column-major, 4th row dropped.
 Xf parse_matrix(const Node& n) {
-    std::vector<float> v = parse_floats(n.contents);
-    if (v.size() != 16)
-        throw std::runtime_error("psy parse error: Transform should be sixteen numbers at byte " +
-                                 std::to_string(n.offset));
+    std::vector<float> v = parse_floats_exact(n, 16, "Transform should be sixteen numbers");
     Xf m;
     m.X = v3(v[0], v[1], v[2]);
     m.Y = v3(v[4], v[5], v[6]);
@@ -411,19 +444,16 @@ SceneIR parse_scene(const Node& tree) {
         for (auto& c : rs->children) {
             if (!c.is_leaf) continue;
             if (c.type == "Resolution") {
-                auto v = parse_uints(c.contents);
-                if (v.size() != 2) throw std::runtime_error("Resolution should be '[width height]'.");
+                auto v = parse_uints_exact(c.contents, 2, "Resolution should be '[width height]'.");
                 sc.res_x = v[0];
                 sc.res_y = v[1];
                 fr = true;
             } else if (c.type == "SamplesPerPixel") {
-                auto v = parse_uints(c.contents);
-                if (v.size() != 1) throw std::runtime_error("SamplesPerPixel should be '[samples]'.");
+                auto v = parse_uints_exact(c.contents, 1, "SamplesPerPixel should be '[samples]'.");
                 sc.spp = v[0];
                 fs = true;
             } else if (c.type == "Seed") {
-                auto v = parse_uints(c.contents);
-                if (v.size() != 1) throw std::runtime_error("Seed should be '[seed]'.");
+                auto v = parse_uints_exact(c.contents, 1, "Seed should be '[seed]'.");
                 sc.seed = v[0];
             }
         }
@@ -495,6 +525,49 @@ std::vector<SceneIR> load_psy_text(const std::string& text) {
     lx.skip_ws_comments();
     if (lx.p < text.size()) lx.fail("unexpected text", lx.p);
     return scenes;
+}
+
+
+// ---- test hooks (tests/test_parse_semantics.py mirrors the reference's own parser tests with them)
+// Canonical text of the parsed tree: `Type{...}` / `Type $ident{...}` / `Type[contents]`, siblings separated by ';'.
+static void dump_node(const Node& n, std::string& out) {
+    out += n.type;
+    if (n.has_ident) out += " " + n.ident;
+    if (n.is_leaf) {
+        out += "[" + n.contents + "]";
+    } else {
+        out += "{";
+        for (size_t i = 0; i < n.children.size(); ++i) {
+            if (i) out += ";";
+            dump_node(n.children[i], out);
+        }
+        out += "}";
+    }
+}
+std::string datatree_dump(const std::string& text) {
+    Lexer lx(text);
+    std::string out;
+    bool first = true;
+    for (;;) {
+        Node n;
+        if (!lx.parse_node(n)) break;
+        if (!first) out += ";";
+        first = false;
+        dump_node(n, out);
+    }
+    lx.skip_ws_comments();
+    if (lx.p != text.size()) lx.fail("unexpected text", lx.p);
+    return out;
+}
+size_t test_parse_floats(const std::string& text, float* out, size_t cap, size_t* rest) {
+    std::vector<float> v = parse_floats(text, rest);
+    for (size_t i = 0; i < v.size() && i < cap; ++i) out[i] = v[i];
+    return v.size();
+}
+size_t test_parse_uints(const std::string& text, uint32_t* out, size_t cap, size_t* rest) {
+    std::vector<uint32_t> v = parse_uints(text, rest);
+    for (size_t i = 0; i < v.size() && i < cap; ++i) out[i] = v[i];
+    return v.size();
 }
 
 }  // namespace psyh
