@@ -105,6 +105,12 @@ def test_lerp_slice_known_answers():
     assert lib.oracle_lerp_slice_f32(two, 2, 0.0) == 1.0
     assert lib.oracle_lerp_slice_f32(two, 2, 1.0) == 2.0
     assert lib.oracle_lerp_slice_f32(two, 2, 0.5) == 1.5
+    # lerp_point_1..3, lerp_normal_1..3, lerp_vector_1..3 (lerp.rs:243-320): (1, 2, 1) -> (-2, 1, -1), component-wise
+    for a, b, mid in ((1.0, -2.0, -0.5), (2.0, 1.0, 1.5), (1.0, -1.0, 0.0)):
+        pair = (C.c_float * 2)(a, b)
+        assert lib.oracle_lerp_slice_f32(pair, 2, 0.0) == a
+        assert lib.oracle_lerp_slice_f32(pair, 2, 1.0) == b
+        assert lib.oracle_lerp_slice_f32(pair, 2, 0.5) == mid
 
 
 def test_ulp_helpers():
