@@ -1568,4 +1568,24 @@ int oracle_tri_intersect(const float* orig, const float* dir, float max_t, const
     return hit ? 1 : 0;
 }
 
+// math3d's vector / normal / point unit tests (sub_crates/math3d/src/{vector,normal,point}.rs): op = 0 add, 1 sub,
+// 2 mul scalar (b[0]), 3 div scalar (b[0]), 4 cross, 5 normalized; scalar results: 0 dot, 1 length, 2 length2
+void oracle_vec3_op(int op, const float* a, const float* b, float* out) {
+    const V3 x = mk(a[0], a[1], a[2]), y = b ? mk(b[0], b[1], b[2]) : mk(0, 0, 0);
+    V3 r = x;
+    switch (op) {
+        case 0: r = x + y; break;
+        case 1: r = x - y; break;
+        case 2: r = x * b[0]; break;
+        case 3: r = x / b[0]; break;
+        case 4: r = cross(x, y); break;
+        default: r = normalized(x); break;
+    }
+    out[0] = r.x, out[1] = r.y, out[2] = r.z;
+}
+float oracle_vec3_scalar(int op, const float* a, const float* b) {
+    const V3 x = mk(a[0], a[1], a[2]), y = b ? mk(b[0], b[1], b[2]) : mk(0, 0, 0);
+    return op == 0 ? dot(x, y) : (op == 1 ? length(x) : length2(x));
+}
+
 }  // extern "C"

@@ -4,7 +4,7 @@ path and against the self-derived vectors of SURVEY.md 10.  CPU o
 Reference tests restated here (file:line in /root/reference):
   sub_crates/math3d/src/transform.rs:153-177   multiply_test, inverse_test
   sub_crates/math3d/src/point.rs:166-201       mul_matrix_1, mul_matrix_3
-  sub_crates/math3d/src/vector.rs:220-236      mul_matrix_1
+  sub_crates/math3d/src/vector.rs:190-290      add, sub, mul_scalar, mul_matrix_1, div, length, length2, normalized, dot, cross
   sub_crates/math3d/src/normal.rs:209-220      mul_matrix_1 (<= 4 ulp)
   src/lerp.rs:140-322                          lerp1-3, lerp_slice1-6, lerp_matrix, lerp_point
   src/fp_utils.rs:84-131                       inc/dec ulp tests
@@ -69,6 +69,34 @@ def test_point_vector_normal_times_matrix():
     want = np.array([-4.0625, 1.78125, -0.03125], dtype=np.float32)
     ulps = np.abs(n.view(np.int32) - want.view(np.int32))
     assert ulps.max() <= 4
+
+
+def test_vector_arithmetic_known_answers():
+    """sub_crates/math3d/src/vector.rs:190-290 (add, sub, mul_scalar, div, length, length2, normalized, dot_test,
+    cross_test); normal.rs and point.rs hold the same cases for their types."""
+    lib = O.load()
+    lib.oracle_vec3_scalar.restype = C.c_float
+
+    def op(k, a, b=None):
+        out = (C.c_float * 3)()
+        lib.oracle_vec3_op(k, (C.c_float * 3)(*a), (C.c_float * 3)(*b) if b else None, out)
+        return list(out)
+
+    def scalar(k, a, b=None):
+        return lib.oracle_vec3_scalar(k, (C.c_float * 3)(*a), (C.c_float * 3)(*b) if b else None)
+
+    v1, v2 = (1.0, 2.0, 3.0), (1.5, 4.5, 2.5)
+    assert op(0, v1, v2) == [2.5, 6.5, 5.5]
+    assert op(1, v1, v2) == [-0.5, -2.5, 0.5]
+    assert op(2, v1, (2.0, 0, 0)) == [2.0, 4.0, 6.0]
+    assert op(3, v1, (2.0, 0, 0)) == [0.5, 1.0, 1.5]
+    assert abs(scalar(1, v1) - 3.7416573867739413) < 0.000001
+    assert scalar(2, v1) == 14.0
+    n = op(5, v1)
+    for got, want in zip(n, (0.2672612419124244, 0.5345224838248488, 0.8017837257372732)):
+        assert abs(got - want) < 0.000001
+    assert scalar(0, v1, v2) == 18.0
+    assert op(4, (1.0, 0.0, 0.0), (0.0, 1.0, 0.0)) == [0.0, 0.0, 1.0]
 
 
 def test_point_matrix_composition():
