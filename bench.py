@@ -371,13 +371,19 @@ def main():
     scene.pin()
     e2e_img = torch.empty((ry, rx, 3), dtype=torch.float32, pin_memory=True).numpy() if rank == 0 else None
 
+    e2e_phases = []
+
     def e2e_step():
+        tp = [time.perf_counter()]
         rr = api.Renderer(scene, device=local_rank)          # H2D: the whole scene description
+        tp.append(time.perf_counter())
         if world == 1:
             img_, st_ = rr.render(max_samples_per_bucket=args.pool, out=e2e_img)   # D2H: the finished image
+            tp.append(time.perf_counter())
         else:
             st_ = rr.render_shard(rank, world, max_samples_per_bucket=args.pool, work_queue_key=wq_key,
                                   buckets_per_gpu=args.buckets_per_gpu)
+            tp.append(time.perf_counter())
             ptr_, n_ = rr.device_image()
 
             class _W:
@@ -385,8 +391,12 @@ def main():
             t_ = torch.as_tensor(_W(), device=torch.device("cuda", local_rank))
             dist.reduce(t_, dst=0, op=dist.ReduceOp.SUM)
             torch.cuda.synchronize()
+            tp.append(time.perf_counter())
             img_ = rr.fetch_image(out=e2e_img) if rank == 0 else None          # D2H on rank 0
+            tp.append(time.perf_counter())
         rr.close()
+        tp.append(time.perf_counter())
+        e2e_phases.append([round((b - a) * 1e3, 2) for a, b in zip(tp, tp[1:])])
         return img_, st_
     e2e_step()
     barrier()
@@ -398,6 +408,8 @@ def main():
         e_rays += int(st2["ray_count"])
     barrier()
     e_s = time.perf_counter() - t0
+    if os.environ.get("PSY_E2E_PHASES"):  # upload | render | (reduce | fetch |) close, ms per step, every rank
+        print(f"[e2e phases] rank {rank}: {e2e_phases}", file=sys.stderr, flush=True)
     et = torch.tensor([e_s, float(e_rays)], dtype=torch.float64, device="cuda")
     if world > 1:
         emax = et.clone()

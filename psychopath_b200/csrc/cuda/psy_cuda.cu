@@ -367,6 +367,25 @@ struct HostPath {
     std::vector<HXf> keys;  // composed keys (empty = none)
 };
 
+// [0, n) in contiguous pieces on the host's cores (pieces of at least `grain`); f(begin, end)
+template <typename F>
+void host_parallel_for(size_t n, size_t grain, F f) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = std::min<size_t>(std::min<unsigned>(hw ? hw : 1u, 16u), (n + grain - 1) / std::max<size_t>(grain, 1));
+    if (nt <= 1) {
+        if (n) f((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = (n + nt - 1) / nt;
+    for (size_t t = 0; t < nt; ++t) {
+        const size_t b = t * per, e = std::min(n, b + per);
+        if (b >= e) break;
+        th.emplace_back([=]() { f(b, e); });
+    }
+    for (auto& x : th) x.join();
+}
+
 int32_t validate(const PsySceneDesc* s) {
     if (!s) return fail(PSY_ERR_INVALID, "null scene description");
     if (s->abi_version != PSY_ABI_VERSION) return fail(PSY_ERR_INVALID, "PsySceneDesc.abi_version mismatch");
@@ -389,16 +408,37 @@ int32_t validate(const PsySceneDesc* s) {
         if (o.kind == PSY_OBJECT_MESH ? o.index >= s->n_meshes : o.index >= s->n_lights)
             return fail(PSY_ERR_INVALID, "object index out of range");
     }
-    for (uint32_t i = 0; i < s->n_nodes; ++i) {
-        const PsyBvh4Node& n = s->nodes[i];
-        if (n.n_children < 2 || n.n_children > 4 || n.traversal_code >= 48 || n.n_keys == 0)
-            return fail(PSY_ERR_INVALID, "malformed BVH4 node");
-        if (n.n_keys > 1 && (uint64_t)n.key_base + n.n_keys > s->n_motion_bounds)
-            return fail(PSY_ERR_INVALID, "BVH4 node key range");
-        for (uint32_t c = 0; c < n.n_children; ++c) {
-            uint32_t r = n.child[c];
-            if (r == PSY_NONE) return fail(PSY_ERR_INVALID, "BVH4 node with missing child");
-            if (!PSY_CHILD_IS_LEAF(r) && r >= s->n_nodes) return fail(PSY_ERR_INVALID, "BVH4 child out of range");
+    {
+        // every node once, on all host cores (the scene is validated at every upload: 57 MB of nodes in the headline scene)
+        std::atomic<int> bad{0};
+        host_parallel_for(s->n_nodes, 32768, [&](size_t b0, size_t e0) {
+            int mine = 0;
+            for (size_t i = b0; i < e0 && !mine; ++i) {
+                const PsyBvh4Node& n = s->nodes[i];
+                if (n.n_children < 2 || n.n_children > 4 || n.traversal_code >= 48 || n.n_keys == 0) {
+                    mine = 1;
+                    break;
+                }
+                if (n.n_keys > 1 && (uint64_t)n.key_base + n.n_keys > s->n_motion_bounds) mine = 2;
+                for (uint32_t c = 0; c < n.n_children; ++c) {
+                    uint32_t r = n.child[c];
+                    if (r == PSY_NONE)
+                        mine = 3;
+                    else if (!PSY_CHILD_IS_LEAF(r) && r >= s->n_nodes)
+                        mine = 4;
+                }
+            }
+            if (mine) {
+                int expect = 0;
+                bad.compare_exchange_strong(expect, mine);
+            }
+        });
+        switch (bad.load()) {
+            case 1: return fail(PSY_ERR_INVALID, "malformed BVH4 node");
+            case 2: return fail(PSY_ERR_INVALID, "BVH4 node key range");
+            case 3: return fail(PSY_ERR_INVALID, "BVH4 node with missing child");
+            case 4: return fail(PSY_ERR_INVALID, "BVH4 child out of range");
+            default: break;
         }
     }
     for (uint32_t i = 0; i < s->n_assemblies; ++i) {
@@ -1123,10 +1163,31 @@ static int32_t scene_create_one(PsyContext* ctx, const PsySceneDesc* s, PsyScene
     // k_trace_pool's node blob (dscene.cuh): where every node starts, in 16-byte units, and the re-encoded references
     std::vector<uint32_t> unit_off(s->n_nodes);
     uint64_t blob_units = 0;
-    for (uint32_t i = 0; i < s->n_nodes; ++i) {
-        unit_off[i] = (uint32_t)blob_units;
-        blob_units += 2u + 6u * (uint64_t)s->nodes[i].n_keys;
+    {
+        // prefix sum of the node sizes in chunks: sizes per chunk, chunk starts, then the offsets (parallel passes)
+        const size_t chunk = 32768, n_chunks = ((size_t)s->n_nodes + chunk - 1) / chunk;
+        std::vector<uint64_t> chunk_units(n_chunks + 1, 0);
+        host_parallel_for(n_chunks, 1, [&](size_t c0, size_t c1) {
+            for (size_t c = c0; c < c1; ++c) {
+                uint64_t u = 0;
+                const size_t e = std::min<size_t>(s->n_nodes, (c + 1) * chunk);
+                for (size_t i = c * chunk; i < e; ++i) u += 2u + 6u * (uint64_t)s->nodes[i].n_keys;
+                chunk_units[c + 1] = u;
+            }
+        });
+        for (size_t c = 0; c < n_chunks; ++c) chunk_units[c + 1] += chunk_units[c];
+        blob_units = chunk_units[n_chunks];
         if (blob_units > (uint64_t)NODE2_OFF_MASK) return fail(PSY_ERR_LIMIT, "BVH4 node store exceeds 4 GB");
+        host_parallel_for(n_chunks, 1, [&](size_t c0, size_t c1) {
+            for (size_t c = c0; c < c1; ++c) {
+                uint64_t u = chunk_units[c];
+                const size_t e = std::min<size_t>(s->n_nodes, (c + 1) * chunk);
+                for (size_t i = c * chunk; i < e; ++i) {
+                    unit_off[i] = (uint32_t)u;
+                    u += 2u + 6u * (uint64_t)s->nodes[i].n_keys;
+                }
+            }
+        });
     }
     auto blob_ref = [&](uint32_t c) -> uint32_t {
         if (c & PSY_CHILD_LEAF_BIT) return c;  // leaves and PSY_NONE
@@ -1171,14 +1232,16 @@ static int32_t scene_create_one(PsyContext* ctx, const PsySceneDesc* s, PsyScene
         path_static[2 * i + 1] = path_inv[i];
     }
 
-    std::vector<float4> normals4(s->n_vert_keys);
+    std::vector<float4> normals4;
     bool any_normals = false;
     for (uint32_t m = 0; m < s->n_meshes; ++m) any_normals |= s->meshes[m].has_normals != 0;
-    if (any_normals)
-        for (uint32_t i = 0; i < s->n_vert_keys; ++i)
-            normals4[i] = make_float4(s->normals[3 * (size_t)i], s->normals[3 * (size_t)i + 1], s->normals[3 * (size_t)i + 2], 0.0f);
-    else
-        normals4.clear();
+    if (any_normals) {
+        normals4.resize(s->n_vert_keys);
+        host_parallel_for(s->n_vert_keys, 65536, [&](size_t b0, size_t e0) {
+            for (size_t i = b0; i < e0; ++i)
+                normals4[i] = make_float4(s->normals[3 * i], s->normals[3 * i + 1], s->normals[3 * i + 2], 0.0f);
+        });
+    }
 
     // light instance -> index of the same instance inside its assembly's instance list
     std::vector<uint32_t> light_local(s->n_light_instances, PSY_NONE);
