@@ -178,11 +178,13 @@ Scene $nested {
 """
 
 
-def random_scene_text(seed):
+def random_scene_text(seed, many_keys=False):
     """A seeded random scene in the reference's text format, for the fuzz parity tests: every feature the path reads
     (time keys on cameras, vertices, normals, transforms, light sizes and colours; Lambert / GGX / Emit shaders;
     rec709 / blackbody / color_temperature colours; sphere, rectangle and distant lights; assemblies nested up to
-    three deep, instanced with and without transforms) in combinations nobody wrote by hand."""
+    three deep, instanced with and without transforms) in combinations nobody wrote by hand.  many_keys: meshes and
+    instances with 9 and 12 time keys as well (BVH nodes of eight or more keys take their own fetch path in the trace
+    kernel, and the device BVH build hands meshes of more than eight keys back to the host)."""
     import random
     rnd = random.Random(seed)
 
@@ -230,7 +232,7 @@ def random_scene_text(seed):
         return f"SurfaceShader ${name} {{ Type [Emit] Color {colour(0.2, 2.0)} }}"
 
     def mesh(name):
-        n_keys = rnd.choice([1, 1, 2, 3])
+        n_keys = rnd.choice([1, 2, 9, 12] if many_keys else [1, 1, 2, 3])
         with_normals = rnd.random() < 0.4
         kind = rnd.choice(["patch", "patch", "box", "fan"])
         if kind == "patch":
@@ -310,7 +312,7 @@ def random_scene_text(seed):
         spread = 4.0 if depth == 0 else 1.5
         for name, kind in things:
             for _ in range(rnd.randint(1, 3 if kind != "light" else 2)):
-                n_keys = rnd.choice([0, 1, 1, 2, 3])
+                n_keys = rnd.choice([0, 1, 2, 9] if many_keys else [0, 1, 1, 2, 3])
                 bind = f" SurfaceShaderBind [${rnd.choice(shaders)}]" if kind == "mesh" else ""
                 z = -rnd.uniform(1.5, 4.0) if kind == "light" else None  # (the fixtures' "up" is -z in instance space)
                 xf = xform_keys(n_keys, spread=spread, z=z, scale=1.0 if kind == "light" else None) if n_keys else ""

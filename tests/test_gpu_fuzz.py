@@ -63,3 +63,35 @@ def test_random_scene_product_build_within_the_gate(seed):
     rel_l2 = np.linalg.norm(gimg - oimg) / max(np.linalg.norm(oimg), 1e-20)
     print(f"[fuzz parity] seed {seed}: rel-L2 {rel_l2:.3e}")
     assert rel_l2 <= 2e-3
+
+
+@pytest.mark.parametrize("seed", range(100, 108))
+def test_random_scene_with_nine_and_twelve_time_keys(seed):
+    """Meshes and instance transforms with more than eight time keys: the trace kernel's node references hold the key
+    count only up to seven; beyond that it comes from the node header (dpool.cuh, kc == 7)."""
+    scene = api.Scene.from_psy_string(random_scene_text(seed, many_keys=True))
+    d = scene.desc.contents
+    assert max(d.nodes[i].n_keys for i in range(d.n_nodes)) >= 8
+    r = api.Renderer(scene, strict=True)
+    gs, st = r.render_bucket_samples(0, 0, d.res_x, d.res_y, d.spp, d.seed)
+    with O.strict_math():
+        _, osamp, ost = O.render_bucket(scene.desc, 0, 0, d.res_x, d.res_y, d.spp, d.seed, want_samples=True)
+    assert st["ray_count"] == ost.ray_count
+    ok = same_or_both_nan(gs, osamp)
+    assert ok.all(), f"{(~ok).any(axis=-1).sum()} of {ok.shape[0]} samples differ"
+    rays = probe_rays(scene, n_random=6000, seed=2000 + seed)
+    gh = api.Tracer(scene).trace(rays)
+    oh = O.trace_rays(scene.desc, rays)[0]
+    for k in ("kind", "prim_id", "inst_id", "path_id", "t", "b0", "b1", "b2"):
+        assert np.array_equal(gh[k], oh[k]), k
+    # the device BVH build refuses meshes of more than eight keys; the scene must still build (topology path) and hit the same
+    api.enable_gpu_build(min_tris=4, mode="bvh4")
+    try:
+        gpu = api.Scene.from_psy_string(random_scene_text(seed, many_keys=True))
+    finally:
+        api.disable_gpu_build()
+    closest = (rays["flags"] & 1) == 0
+    bh = api.Tracer(gpu).trace(rays)
+    assert np.array_equal(bh["kind"][closest], oh["kind"][closest])
+    hit = closest & (oh["kind"] == abi.HIT_TRIANGLE)
+    assert np.array_equal(bh["t"][hit], oh["t"][hit])
