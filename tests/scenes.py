@@ -341,3 +341,34 @@ def random_scene_text(seed, many_keys=False):
             f"        ApertureRadius [{f(rnd.choice([0.0, 0.03, 0.1]))}]\n" + "\n".join(cam) + "\n    }\n"
             "    World {\n" + "\n".join(world) + "\n    }\n"
             "    Assembly {\n" + floor + assembly(0, "        ") + "\n    }\n}\n")
+
+
+def edge_case_texts():
+    """Small scenes at the edges of the path: nothing to hit, nothing to light with, a mesh that is a single leaf,
+    only a distant light, an emitter as the only light source; odd resolutions and sample counts."""
+    HEAD = """Scene $edge {
+        Output { Path ["edge.png"] }
+        RenderSettings { Resolution [%d %d] SamplesPerPixel [%d] Seed [3] }
+        Camera { Fov [50.0] FocalDistance [9.0] ApertureRadius [0.0] Transform [1 0 0 0  0 0 1 0  0 1 0 0  0 -9 2 1] }
+        World { BackgroundShader { Type [Color] Color [rec709, 0.3 0.4 0.5] } %s }
+        Assembly { %s }
+    }
+    """
+    TRI = """SurfaceShader $s { Type [Lambert] Color [rec709, 0.7 0.6 0.5] }
+            MeshSurface $t { Vertices [-2 0 -1  2 0 -1  0 0 3] FaceVertCounts [3] FaceVertIndices [0 1 2] }
+            Instance { Data [$t] SurfaceShaderBind [$s] }"""
+    EMIT = """SurfaceShader $e { Type [Emit] Color [rec709, 2 1 0.5] }
+            SurfaceShader $s { Type [GGX] Color [rec709, 0.7 0.6 0.5] Roughness [0.3] Fresnel [0.4] }
+            MeshSurface $t { Vertices [-2 0 -1  2 0 -1  0 0 3] FaceVertCounts [3] FaceVertIndices [0 1 2] }
+            MeshSurface $f { Vertices [-6 -6 -1  6 -6 -1  6 6 -1  -6 6 -1] FaceVertCounts [4] FaceVertIndices [0 1 2 3] }
+            Instance { Data [$t] SurfaceShaderBind [$e] }
+            Instance { Data [$f] SurfaceShaderBind [$s] }"""
+    SUN = "DistantDiskLight $sun { Direction [-0.3 0.4 -0.8] Color [rec709, 1.5 1.4 1.2] Radius [0.05] }"
+    cases = {
+        "background_only": HEAD % (37, 23, 3, "", ""),
+        "one_triangle_no_lights": HEAD % (37, 23, 3, "", TRI),
+        "one_triangle_sun_only": HEAD % (40, 24, 1, SUN, TRI),
+        "emitter_lights_a_ggx_floor": HEAD % (33, 21, 5, "", EMIT),
+        "emitter_and_sun": HEAD % (32, 20, 4, SUN, EMIT),
+    }
+    return cases
