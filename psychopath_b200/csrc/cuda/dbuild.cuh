@@ -1,14 +1,14 @@
-// dbuild.cuh — SURVEY.md N3: the topology of a mesh BVH built on the GPU (LBVH).
+// dbuild.cuh — SURVEY.md N3: a mesh's BVH built on the GPU.
 //
 // The reference builds its binary BVH top-down on one thread with a binned SAH (src/accel/bvh_base.rs:96-215,
 // objects_split.rs:153-238): seconds at 10 M triangles.  This is the build for scenes whose build time matters
-// (previews, animation): triangles are ordered along a 63-bit Morton curve of their centroids (cub radix sort), the
-// binary radix tree over the sorted triangles is built in one parallel pass (Karras 2012), and every subtree of at
-// most `tris_per_leaf` triangles (the reference's 3, triangle_mesh.rs:17) becomes one leaf.  Only the TOPOLOGY comes from
-// here — triangle order, children, split axes, depth; the host then derives the time-sampled bounds, the 1.4x
-// union rule and the BVH2 -> BVH4 collapse exactly as for its own SAH trees (bvh_build.h: build_bvh4_from_topology),
-// so the trace kernels and the oracle read the same node format either way.  A different tree means different
-// visit counts and tie-breaks, never different hits: tests/test_gpu_build.py.
+// (previews, animation): triangles are ordered along a 63-bit Morton curve of their centroids (cub radix sort); the
+// binary tree over the sorted triangles comes from PLOC (below; or Karras' radix tree, 2012, in one parallel pass), and
+// every subtree of at most `tris_per_leaf` triangles (the reference's 3, triangle_mesh.rs:17) becomes one leaf.  The
+// second half of the file turns that topology into the reference's BVH4 — time-sampled bounds, the 1.4x union rule,
+// the BVH2 -> BVH4 collapse — in the host builder's arithmetic (bvh_build.h), so the trace kernels and the oracle read
+// the same node format whichever side built it.  A different tree means different visit counts and tie-breaks, never
+// different hits: tests/test_gpu_build.py.
 #pragma once
 #include <cub/cub.cuh>
 
@@ -193,6 +193,201 @@ __global__ void __launch_bounds__(256) k_lbvh_depth(const int32_t* __restrict__ 
     }
     dep = __reduce_max_sync(0xffffffffu, dep);
     if ((threadIdx.x & 31u) == 0u && dep) atomicMax(depth, dep);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PLOC (Meister & Bittner, "Parallel Locally-Ordered Clustering for Bounding Volume Hierarchy Construction", 2018):
+// the binary tree of better quality than the radix tree, from the same Morton-sorted triangles.  Clusters start as
+// the sorted triangles (bounds at shutter time 0.5, the host builder's criterion); every round each cluster looks
+// PLOC_RADIUS places to either side for the partner whose union with it has the smallest surface area, mutual choices
+// merge into a new node, the cluster list is compacted in order, until one cluster is left.  Everything is
+// deterministic: partners are compared by (area, lower place, higher place), new nodes are numbered by a scan.
+// Ids: < n a triangle (its place in the sorted list), >= n the internal node id - n.
+#ifndef PSY_PLOC_RADIUS
+#define PSY_PLOC_RADIUS 16
+#endif
+constexpr int PLOC_RADIUS = PSY_PLOC_RADIUS;
+
+struct PlocBox {
+    float mn[3], mx[3];
+};
+PSY_DEV float ploc_union_area(const PlocBox& a, const PlocBox& b) {
+    const float dx = fmaxf(a.mx[0], b.mx[0]) - fminf(a.mn[0], b.mn[0]);
+    const float dy = fmaxf(a.mx[1], b.mx[1]) - fminf(a.mn[1], b.mn[1]);
+    const float dz = fmaxf(a.mx[2], b.mx[2]) - fminf(a.mn[2], b.mn[2]);
+    return (dx * dy) + (dy * dz) + (dz * dx);
+}
+// bounds of the sorted triangles at shutter time 0.5
+__global__ void __launch_bounds__(256) k_ploc_init(const float* __restrict__ verts, uint32_t n_keys,
+                                                   const uint32_t* __restrict__ tri_idx, const uint32_t* __restrict__ order,
+                                                   uint32_t n, PlocBox* __restrict__ box, uint32_t* __restrict__ cid) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t t = order[i];
+    const uint32_t v[3] = {tri_idx[3 * (size_t)t], tri_idx[3 * (size_t)t + 1], tri_idx[3 * (size_t)t + 2]};
+    uint32_t k0 = 0, k1 = 0;
+    float a = 0.0f;
+    if (n_keys > 1) {
+        const float tmp = 0.5f * (float)(n_keys - 1);
+        k0 = (uint32_t)tmp;
+        a = tmp - (float)k0;
+        k1 = min(k0 + 1u, n_keys - 1u);
+    }
+    PlocBox b;
+    for (int d = 0; d < 3; ++d) {
+        float mn[2], mx[2];
+        const uint32_t ks[2] = {k0, k1};
+        for (int q = 0; q < 2; ++q) {
+            const float p0 = verts[((size_t)v[0] * n_keys + ks[q]) * 3 + d], p1 = verts[((size_t)v[1] * n_keys + ks[q]) * 3 + d],
+                        p2 = verts[((size_t)v[2] * n_keys + ks[q]) * 3 + d];
+            mn[q] = fminf(p0, fminf(p1, p2));
+            mx[q] = fmaxf(p0, fmaxf(p1, p2));
+        }
+        b.mn[d] = (mn[0] * (1.0f - a)) + (mn[1] * a);
+        b.mx[d] = (mx[0] * (1.0f - a)) + (mx[1] * a);
+    }
+    box[i] = b;
+    cid[i] = i;
+}
+// nearest partner of every cluster within the radius; the block's clusters and their halo are staged in shared memory
+__global__ void __launch_bounds__(256) k_ploc_nearest(const PlocBox* __restrict__ box, uint32_t m, uint32_t* __restrict__ nn) {
+    __shared__ PlocBox tile[256 + 2 * PLOC_RADIUS];
+    const int base = (int)(blockIdx.x * blockDim.x) - PLOC_RADIUS;
+    for (int s = (int)threadIdx.x; s < 256 + 2 * PLOC_RADIUS; s += 256) {
+        const int g = base + s;
+        if (g >= 0 && g < (int)m) tile[s] = box[g];
+    }
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const PlocBox me = tile[threadIdx.x + PLOC_RADIUS];
+    float best = CUDART_INF_F;
+    uint32_t best_j = 0xFFFFFFFFu;
+    const int lo = max((int)i - PLOC_RADIUS, 0), hi = min((int)i + PLOC_RADIUS, (int)m - 1);
+    for (int j = lo; j <= hi; ++j) {
+        if (j == (int)i) continue;
+        const float a = ploc_union_area(me, tile[j - base]);
+        // order of candidate pairs: (area, lower place, higher place) — the same from both ends of a pair
+        bool better = a < best;
+        if (a == best && best_j != 0xFFFFFFFFu) {
+            const uint32_t lo_new = min(i, (uint32_t)j), hi_new = max(i, (uint32_t)j);
+            const uint32_t lo_old = min(i, best_j), hi_old = max(i, best_j);
+            better = lo_new < lo_old || (lo_new == lo_old && hi_new < hi_old);
+        }
+        if (better) best = a, best_j = (uint32_t)j;
+    }
+    nn[i] = best_j;
+}
+// lead[i] = 1 where cluster i merges with its partner and is the lower of the two; gone[i] = 1 for the higher one
+__global__ void __launch_bounds__(256) k_ploc_flags(const uint32_t* __restrict__ nn, uint32_t m, uint32_t* __restrict__ lead,
+                                                    uint32_t* __restrict__ stay) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t j = nn[i];
+    const bool mutual = j != 0xFFFFFFFFu && nn[j] == i;
+    lead[i] = (mutual && i < j) ? 1u : 0u;
+    stay[i] = (mutual && i > j) ? 0u : 1u;
+}
+// merge the pairs and compact the cluster list in order
+__global__ void __launch_bounds__(256) k_ploc_merge(const PlocBox* __restrict__ box, const uint32_t* __restrict__ cid,
+                                                    const uint32_t* __restrict__ nn, const uint32_t* __restrict__ lead,
+                                                    const uint32_t* __restrict__ lead_at, const uint32_t* __restrict__ stay,
+                                                    const uint32_t* __restrict__ stay_at, uint32_t m, uint32_t n,
+                                                    uint32_t node_base, PlocBox* __restrict__ box_out, uint32_t* __restrict__ cid_out,
+                                                    uint32_t* __restrict__ left, uint32_t* __restrict__ right,
+                                                    uint8_t* __restrict__ axis, uint32_t* __restrict__ cnt,
+                                                    uint32_t* __restrict__ parent) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m || !stay[i]) return;
+    PlocBox b = box[i];
+    uint32_t id = cid[i];
+    if (lead[i]) {
+        const uint32_t j = nn[i];
+        const PlocBox o = box[j];
+        uint32_t a_id = id, b_id = cid[j];
+        // split axis = where the two centres are furthest apart; the child with the lower centre goes left
+        float sep[3];
+        for (int d = 0; d < 3; ++d) sep[d] = (o.mn[d] + o.mx[d]) - (b.mn[d] + b.mx[d]);
+        int ax = 0;
+        if (fabsf(sep[1]) > fabsf(sep[ax])) ax = 1;
+        if (fabsf(sep[2]) > fabsf(sep[ax])) ax = 2;
+        if (sep[ax] < 0.0f) {
+            const uint32_t t = a_id;
+            a_id = b_id, b_id = t;
+        }
+        const uint32_t node = node_base + lead_at[i];  // internal node index
+        left[node] = a_id, right[node] = b_id, axis[node] = (uint8_t)ax;
+        cnt[node] = (a_id < n ? 1u : cnt[a_id - n]) + (b_id < n ? 1u : cnt[b_id - n]);
+        parent[a_id] = node, parent[b_id] = node;
+        for (int d = 0; d < 3; ++d) b.mn[d] = fminf(b.mn[d], o.mn[d]), b.mx[d] = fmaxf(b.mx[d], o.mx[d]);
+        id = n + node;
+    }
+    const uint32_t at = stay_at[i];
+    box_out[at] = b;
+    cid_out[at] = id;
+}
+// The place of every triangle / the first place of every node in the leaf order of the finished tree: walking up,
+// every time the node is a right child its left sibling's triangles come first.  ids as above; parent[] is indexed by id.
+PSY_DEV uint32_t ploc_place(uint32_t id, uint32_t n, uint32_t root_node, const uint32_t* __restrict__ left,
+                            const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ parent, uint32_t* kept_above,
+                            uint32_t per_leaf) {
+    uint32_t pos = 0, above = 0;
+    while (id != n + root_node) {
+        const uint32_t p = parent[id];
+        const uint32_t l = left[p];
+        if (l != id) pos += l < n ? 1u : cnt[l - n];
+        above += cnt[p] > per_leaf ? 1u : 0u;
+        id = n + p;
+    }
+    if (kept_above) *kept_above = above;
+    return pos;
+}
+__global__ void __launch_bounds__(256) k_ploc_order(const uint32_t* __restrict__ order_in, uint32_t n, uint32_t root_node,
+                                                    const uint32_t* __restrict__ left, const uint32_t* __restrict__ cnt,
+                                                    const uint32_t* __restrict__ parent, uint32_t per_leaf,
+                                                    uint32_t* __restrict__ order_out, uint32_t* __restrict__ depth) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t above = 0;
+    if (i < n) {
+        const uint32_t pos = ploc_place(i, n, root_node, left, cnt, parent, &above, per_leaf);
+        order_out[pos] = order_in[i];
+    }
+    above = __reduce_max_sync(0xffffffffu, above);
+    if ((threadIdx.x & 31u) == 0u && above) atomicMax(depth, above);
+}
+// keep[node] = 1 for the nodes that stay internal (more than per_leaf triangles below); start[node] = first place
+__global__ void __launch_bounds__(256) k_ploc_keep(uint32_t n, uint32_t n_nodes, uint32_t root_node,
+                                                   const uint32_t* __restrict__ left, const uint32_t* __restrict__ cnt,
+                                                   const uint32_t* __restrict__ parent, uint32_t per_leaf,
+                                                   uint32_t* __restrict__ keep, uint32_t* __restrict__ start) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    keep[v] = cnt[v] > per_leaf ? 1u : 0u;
+    start[v] = ploc_place(n + v, n, root_node, left, cnt, parent, nullptr, per_leaf);
+}
+// kept nodes, renumbered in reverse creation order (the root is created last: it becomes node 0)
+__global__ void __launch_bounds__(256) k_ploc_emit(uint32_t n, uint32_t n_nodes, uint32_t n_keep, uint32_t root_node,
+                                                   const uint32_t* __restrict__ left, const uint32_t* __restrict__ right,
+                                                   const uint8_t* __restrict__ axis, const uint32_t* __restrict__ cnt,
+                                                   const uint32_t* __restrict__ parent, const uint32_t* __restrict__ keep,
+                                                   const uint32_t* __restrict__ keep_at, const uint32_t* __restrict__ start,
+                                                   uint32_t per_leaf, int32_t* __restrict__ left2, int32_t* __restrict__ right2,
+                                                   uint8_t* __restrict__ axis2) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes || !keep[v]) return;
+    const uint32_t me = n_keep - 1u - keep_at[v];
+    auto ref = [&](uint32_t id) -> int32_t {
+        if (id < n) {
+            const uint32_t pos = ploc_place(id, n, root_node, left, cnt, parent, nullptr, per_leaf);
+            return ~(int32_t)((pos << 2) | 1u);
+        }
+        const uint32_t c = id - n;
+        if (keep[c]) return (int32_t)(n_keep - 1u - keep_at[c]);
+        return ~(int32_t)((start[c] << 2) | cnt[c]);
+    };
+    left2[me] = ref(left[v]);
+    right2[me] = ref(right[v]);
+    axis2[me] = axis[v];
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -1860,7 +1860,86 @@ int32_t lbvh_device_topology(PsyContext* ctx, const float* verts, uint32_t n_ver
                                        L.order.as<uint32_t>(), (int)n_tris, 0, 63, st));
     L.depth = 0;
     L.n_internal = 0;
-    if (n_tris > tris_per_leaf) {
+    // PSY_GPU_BUILDER=lbvh keeps the radix tree; the default is PLOC over the same sorted triangles (dbuild.cuh)
+    const char* builder_env = getenv("PSY_GPU_BUILDER");
+    const bool use_ploc = !(builder_env && std::string(builder_env) == "lbvh");
+    if (n_tris > tris_per_leaf && use_ploc) {
+        const uint32_t n = n_tris, n_nodes = n_tris - 1;
+        DevBuf box_a, box_b, cid_a, cid_b, nn, lead, lead_at, stay, stay_at, left, right, axis, cnt, parent, keep, keep_at, start,
+            order2, ddepth;
+        CK(box_a.alloc((size_t)n * sizeof(PlocBox)));
+        CK(box_b.alloc((size_t)n * sizeof(PlocBox)));
+        CK(cid_a.alloc((size_t)n * 4));
+        CK(cid_b.alloc((size_t)n * 4));
+        CK(nn.alloc((size_t)n * 4));
+        CK(lead.alloc((size_t)n * 4));
+        CK(lead_at.alloc((size_t)n * 4));
+        CK(stay.alloc((size_t)n * 4));
+        CK(stay_at.alloc((size_t)n * 4));
+        CK(left.alloc((size_t)n_nodes * 4));
+        CK(right.alloc((size_t)n_nodes * 4));
+        CK(axis.alloc((size_t)n_nodes));
+        CK(cnt.alloc((size_t)n_nodes * 4));
+        CK(parent.alloc(((size_t)n + n_nodes) * 4));
+        CK(keep.alloc((size_t)n_nodes * 4));
+        CK(keep_at.alloc((size_t)n_nodes * 4));
+        CK(start.alloc((size_t)n_nodes * 4));
+        CK(order2.alloc((size_t)n * 4));
+        CK(ddepth.alloc(4));
+        CK(cudaMemsetAsync(ddepth.p, 0, 4, st));
+        k_ploc_init<<<tb, 256, 0, st>>>(L.verts.as<float>(), n_keys, L.idx.as<uint32_t>(), L.order.as<uint32_t>(), n,
+                                       box_a.as<PlocBox>(), cid_a.as<uint32_t>());
+        DevBuf *bi = &box_a, *bo = &box_b, *ci = &cid_a, *co = &cid_b;
+        uint32_t m = n, node_base = 0;
+        int rounds = 0;
+        while (m > 1) {
+            const unsigned mb = (m + 255) / 256;
+            k_ploc_nearest<<<mb, 256, 0, st>>>(bi->as<PlocBox>(), m, nn.as<uint32_t>());
+            k_ploc_flags<<<mb, 256, 0, st>>>(nn.as<uint32_t>(), m, lead.as<uint32_t>(), stay.as<uint32_t>());
+            CK(cub::DeviceScan::ExclusiveSum(dtmp.p, scan_bytes, lead.as<uint32_t>(), lead_at.as<uint32_t>(), (int)m, st));
+            CK(cub::DeviceScan::ExclusiveSum(dtmp.p, scan_bytes, stay.as<uint32_t>(), stay_at.as<uint32_t>(), (int)m, st));
+            k_ploc_merge<<<mb, 256, 0, st>>>(bi->as<PlocBox>(), ci->as<uint32_t>(), nn.as<uint32_t>(), lead.as<uint32_t>(),
+                                            lead_at.as<uint32_t>(), stay.as<uint32_t>(), stay_at.as<uint32_t>(), m, n, node_base,
+                                            bo->as<PlocBox>(), co->as<uint32_t>(), left.as<uint32_t>(), right.as<uint32_t>(),
+                                            axis.as<uint8_t>(), cnt.as<uint32_t>(), parent.as<uint32_t>());
+            uint32_t last[2] = {0, 0};
+            CK(cudaMemcpyAsync(&last[0], lead.as<uint32_t>() + (m - 1), 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&last[1], lead_at.as<uint32_t>() + (m - 1), 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const uint32_t merges = last[0] + last[1];
+            if (merges == 0 || ++rounds > 4096) return fail(PSY_ERR_CUDA, "PLOC made no progress");
+            m -= merges;
+            node_base += merges;
+            std::swap(bi, bo);
+            std::swap(ci, co);
+        }
+        if (node_base != n_nodes) return fail(PSY_ERR_CUDA, "PLOC node count");
+        const uint32_t root_node = n_nodes - 1;  // created last
+        const unsigned nb = (n_nodes + 255) / 256;
+        k_ploc_order<<<tb, 256, 0, st>>>(L.order.as<uint32_t>(), n, root_node, left.as<uint32_t>(), cnt.as<uint32_t>(),
+                                        parent.as<uint32_t>(), tris_per_leaf, order2.as<uint32_t>(), ddepth.as<uint32_t>());
+        k_ploc_keep<<<nb, 256, 0, st>>>(n, n_nodes, root_node, left.as<uint32_t>(), cnt.as<uint32_t>(), parent.as<uint32_t>(),
+                                       tris_per_leaf, keep.as<uint32_t>(), start.as<uint32_t>());
+        CK(cub::DeviceScan::ExclusiveSum(dtmp.p, scan_bytes, keep.as<uint32_t>(), keep_at.as<uint32_t>(), (int)n_nodes, st));
+        uint32_t last_keep = 0, last_at = 0;
+        CK(cudaMemcpyAsync(&last_keep, keep.as<uint32_t>() + (n_nodes - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&last_at, keep_at.as<uint32_t>() + (n_nodes - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&L.depth, ddepth.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint32_t n_keep = last_keep + last_at;
+        CK(L.left.alloc((size_t)n_keep * 4));
+        CK(L.right.alloc((size_t)n_keep * 4));
+        CK(L.axis.alloc((size_t)n_keep));
+        k_ploc_emit<<<nb, 256, 0, st>>>(n, n_nodes, n_keep, root_node, left.as<uint32_t>(), right.as<uint32_t>(),
+                                       axis.as<uint8_t>(), cnt.as<uint32_t>(), parent.as<uint32_t>(), keep.as<uint32_t>(),
+                                       keep_at.as<uint32_t>(), start.as<uint32_t>(), tris_per_leaf, L.left.as<int32_t>(),
+                                       L.right.as<int32_t>(), L.axis.as<uint8_t>());
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+        L.order = std::move(order2);
+        L.n_internal = n_keep;
+        L.root = 0;
+    } else if (n_tris > tris_per_leaf) {
         const int n_nodes = (int)n_tris - 1;  // of the radix tree over single triangles
         CK(dleft.alloc((size_t)n_nodes * 4));
         CK(dright.alloc((size_t)n_nodes * 4));
