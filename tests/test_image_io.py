@@ -5,6 +5,7 @@ import ctypes as C
 import os
 
 import numpy as np
+import pytest
 
 from psychopath_b200 import abi
 
@@ -47,16 +48,35 @@ def test_png_roundtrip(tmp_path):
     assert np.abs(got[..., 2::-1][..., :3].astype(int) - want.astype(int)).max() <= 1
 
 
-def test_exr_roundtrip(tmp_path):
+@pytest.mark.parametrize("compression", ["zip", "none"])
+@pytest.mark.parametrize("size", [(37, 23), (64, 16), (5, 40)])
+def test_exr_roundtrip(tmp_path, monkeypatch, compression, size):
+    """Half RGB in rec709-E, ZIP-compressed in 16-line blocks (default) or plain scanlines; read back by OpenCV's
+    OpenEXR.  Heights below, at and above a multiple of the block size."""
     import cv2
     h = _lib()
-    img = _image()
+    img = _image(*size)
+    monkeypatch.setenv("PSY_EXR_COMPRESSION", compression)
     p = str(tmp_path / "a.exr")
     assert h.psyh_write_exr(p.encode(), img.ctypes.data, img.shape[1], img.shape[0]) == 0
     got = cv2.imread(p, cv2.IMREAD_UNCHANGED)
     assert got is not None and got.shape[:2] == img.shape[:2]
     want = (img @ M.T).astype(np.float16).astype(np.float32)
     assert np.allclose(got[..., ::-1], want, atol=2e-3)
+
+
+def test_exr_zip_is_smaller_on_a_smooth_image(tmp_path, monkeypatch):
+    import os
+    h = _lib()
+    yy, xx = np.mgrid[0:128, 0:256].astype(np.float32)
+    img = np.ascontiguousarray(np.stack([xx / 256, yy / 128, (xx + yy) / 384], axis=-1).astype(np.float32))
+    sizes = {}
+    for c in ("zip", "none"):
+        monkeypatch.setenv("PSY_EXR_COMPRESSION", c)
+        p = str(tmp_path / f"{c}.exr")
+        assert h.psyh_write_exr(p.encode(), img.ctypes.data, 256, 128) == 0
+        sizes[c] = os.path.getsize(p)
+    assert sizes["zip"] < 0.5 * sizes["none"]
 
 
 def test_bucket_base64_stream():
