@@ -29,6 +29,16 @@ def test_cuda_library_exports_every_declared_symbol():
     assert lib.psy_abi_version() == 2
 
 
+def test_integration_doc_binds_every_declared_symbol():
+    """INTEGRATION.md's reference-side binding (the Rust `extern "C"` block a maintainer would add) names exactly the
+    functions include/psy_cuda.h declares."""
+    header = open(os.path.join(REPO, "include", "psy_cuda.h")).read()
+    declared = set(re.findall(r"\b(psy_[a-z_]+)\s*\(", header)) - {"psy_bucket_cb"}
+    doc = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    bound = set(re.findall(r"pub fn (psy_[a-z_]+)\(", doc))
+    assert bound == declared, bound ^ declared
+
+
 def test_struct_layout_matches_c():
     """Compiles a tiny C program against the header and compares sizeof() with the ctypes mirror."""
     names = ["PsyXform", "PsyBBox", "PsyBBox4", "PsyBvh4Node", "PsyColor", "PsyShader", "PsyMesh", "PsyLight",
