@@ -376,8 +376,9 @@ int32_t psy_device_image(PsyScene* scene, void** dev_ptr, size_t* n_floats);
 
 /* SURVEY.md N3 — the GPU build of a mesh BVH, behind a flag (`psychopath --gpu-build`, api.enable_gpu_build()).
  * Replaces the ORDERING and TOPOLOGY half of BVHBase::from_objects (src/accel/bvh_base.rs:57-215): triangles sorted along
- * a 63-bit Morton curve of their centroids at shutter time 0.5,
- * binary radix tree over the sorted triangles (LBVH), subtrees of at most `tris_per_leaf` (<= 3) triangles as leaves.
+ * a 63-bit Morton curve of their centroids at shutter time 0.5, binary tree over the sorted triangles by parallel
+ * locally-ordered clustering (PLOC; the environment variable PSY_GPU_BUILDER=lbvh selects Karras' radix tree instead),
+ * subtrees of at most `tris_per_leaf` (<= 3) triangles as leaves, triangles in the leaf order of the finished tree.
  * Host arrays in and out:
  *   verts   n_verts * n_keys * 3 floats, the time keys of a vertex contiguous (PsySceneDesc.verts layout)
  *   tri_idx 3 vertex indices per triangle
@@ -394,7 +395,7 @@ int32_t psy_build_mesh_topology(PsyContext* ctx, const float* verts, uint32_t n_
                                 uint8_t* axis, uint32_t* n_internal, int32_t* root, uint32_t* depth);
 
 /* SURVEY.md N3, the whole of it — a mesh's BVH4 built on the device, replacing BVHBase::from_objects
- * (src/accel/bvh_base.rs:57-215) AND BVH4::construct_from_base (src/accel/bvh4.rs:186-358) for that mesh: the LBVH
+ * (src/accel/bvh_base.rs:57-215) AND BVH4::construct_from_base (src/accel/bvh4.rs:186-358) for that mesh: the
  * topology above, then per-node time-sampled bounds (bottom-up, bvh_base.rs:119-132's 1.4x union rule at every node),
  * the BVH2 -> BVH4 collapse with its traversal codes, and the time-sampled child bounds of every BVH4 node.  Same
  * arithmetic as the host builder: given the same topology the nodes are the host's bit for bit, in another order
