@@ -371,4 +371,51 @@ def edge_case_texts():
         "emitter_lights_a_ggx_floor": HEAD % (33, 21, 5, "", EMIT),
         "emitter_and_sun": HEAD % (32, 20, 4, SUN, EMIT),
     }
+    cases["white_furnace_motion_dof"] = furnace_text("Type [Lambert] Color [rec709, 1 1 1]", motion=True, aperture=0.2)
+    cases["ggx_furnace"] = furnace_text("Type [GGX] Color [rec709, 1 1 1] Roughness [0.4] Fresnel [1.0]")
     return cases
+
+
+def furnace_text(shader, motion=False, aperture=0.0):
+    """A convex box in a uniform background and nothing else: a path that hits the box leaves it with its first bounce,
+    so with a white Lambert surface every sample must carry exactly the background's radiance (the white furnace)."""
+    xf = "Transform [0.8 0.6 0 0  -0.6 0.8 0 0  0 0 1 0  0.3 0 0.5 1]"
+    if motion:
+        xf += " Transform [0.6 0.8 0 0  -0.8 0.6 0 0  0 0 1 0  0.5 0.2 0.3 1]"
+    return f"""
+Scene $furnace {{
+    Output {{ Path ["furnace.png"] }}
+    RenderSettings {{ Resolution [48 32] SamplesPerPixel [8] Seed [9] }}
+    Camera {{ Fov [40.0] FocalDistance [9.0] ApertureRadius [{aperture}] Transform [1 0 0 0  0 0 1 0  0 1 0 0  0 -9 1 1] }}
+    World {{ BackgroundShader {{ Type [Color] Color [rec709, 0.5 0.5 0.5] }} }}
+    Assembly {{
+        SurfaceShader $s {{ {shader} }}
+        MeshSurface $box {{
+            Vertices [-1 -1 0  1 -1 0  1 1 0  -1 1 0  -1 -1 2  1 -1 2  1 1 2  -1 1 2]
+            FaceVertCounts [4 4 4 4 4 4]
+            FaceVertIndices [0 3 2 1  4 5 6 7  0 1 5 4  1 2 6 5  2 3 7 6  3 0 4 7]
+        }}
+        Instance {{ Data [$box] SurfaceShaderBind [$s] {xf} }}
+    }}
+}}
+"""
+
+
+def lit_floor_text(world_light="", objects="", instances="", res=(32, 24), spp=16):
+    """A large Lambert floor (albedo 0.6) under a black sky, seen from above, lit by whatever the caller adds: the
+    analytic direct-lighting pins of tests/test_oracle_pins.py."""
+    return f"""
+Scene $nee {{
+    Output {{ Path ["nee.png"] }}
+    RenderSettings {{ Resolution [{res[0]} {res[1]}] SamplesPerPixel [{spp}] Seed [5] }}
+    Camera {{ Fov [35.0] FocalDistance [9.0] ApertureRadius [0.0] Transform [1 0 0 0  0 0.6 0.8 0  0 0.8 -0.6 0  0 -6 5 1] }}
+    World {{ BackgroundShader {{ Type [Color] Color [rec709, 0 0 0] }} {world_light} }}
+    Assembly {{
+        SurfaceShader $grey {{ Type [Lambert] Color [rec709, 0.6 0.6 0.6] }}
+        MeshSurface $floor {{ Vertices [-40 -40 0  40 -40 0  40 40 0  -40 40 0] FaceVertCounts [4] FaceVertIndices [0 1 2 3] }}
+        {objects}
+        Instance {{ Data [$floor] SurfaceShaderBind [$grey] }}
+        {instances}
+    }}
+}}
+"""

@@ -308,3 +308,107 @@ def test_sphere_lambert_boundary_is_where_the_references_nan_comes_from():
                         (0.8665500283241272, 0.4990902245044708)]:
         assert np.isnan(lib.oracle_sphere_lambert(nlcos, rcos, out))
         assert abs(np.float32(out[2]) - (np.float32(np.pi / 2) - np.float32(out[3]))) <= 2.4e-7
+
+
+def test_white_furnace_through_the_integrator():
+    """An analytic pin of the path the reference has no test for: a convex white Lambert box in a uniform background,
+    no lights.  A path that hits the box escapes with its first bounce, and with cosine-weighted sampling the bounce
+    weight is exactly the albedo, so EVERY sample must carry the background's radiance — whatever the box does (motion
+    blur, depth of field).  This ties together camera rays, traversal, robust ray origins (a self-hit would go dark),
+    Lambert sample / pdf (surface_closure.rs:284-332), the miss shader and the Meng upsampling of white.  With albedo
+    0.5 the box's samples are exactly half; GGX creates no energy."""
+    from psychopath_b200 import api
+    from scenes import furnace_text
+
+    def samples(shader, **kw):
+        s = api.Scene.from_psy_string(furnace_text(shader, **kw))
+        d = s.desc.contents
+        _, samp, st = O.render_bucket(s.desc, 0, 0, d.res_x, d.res_y, d.spp, d.seed, want_samples=True)
+        hit_share = st.ray_count / (d.res_x * d.res_y * d.spp) - 1.0
+        return samp.reshape(-1, 4), hit_share
+
+    bg = 0.5
+    for kw in ({}, {"motion": True, "aperture": 0.2}):
+        samp, hit_share = samples("Type [Lambert] Color [rec709, 1 1 1]", **kw)
+        assert 0.15 < hit_share < 0.3                       # a fifth of the paths do go through the box
+        assert np.abs(samp - bg).max() < 3e-4, (samp.min(), samp.max())
+    samp, hit_share = samples("Type [Lambert] Color [rec709, 0.5 0.5 0.5]")
+    half = np.abs(samp - 0.5 * bg).max(axis=1) < 3e-4
+    full = np.abs(samp - bg).max(axis=1) < 3e-4
+    assert (half | full).all() and abs(half.mean() - hit_share) < 1e-6
+    samp, _ = samples("Type [GGX] Color [rec709, 1 1 1] Roughness [0.4] Fresnel [1.0]")
+    assert samp.mean() < bg and samp.max() < bg * 1.5
+
+
+def _lit_floor(**kw):
+    from psychopath_b200 import api
+    from scenes import lit_floor_text
+    s = api.Scene.from_psy_string(lit_floor_text(**kw))
+    d = s.desc.contents
+    rays = O.camera_rays(s.desc, 0, 0, d.res_x, d.res_y, d.spp, d.seed)
+    hits, geo, _ = O.trace_rays(s.desc, rays, want_geo=True)
+    _, samp, _ = O.render_bucket(s.desc, 0, 0, d.res_x, d.res_y, d.spp, d.seed, want_samples=True)
+    on = hits["kind"] == abi.HIT_TRIANGLE
+    assert on.all()  # the floor fills the view
+    return geo["pos"].astype(np.float64), samp.reshape(-1, 4), d.spp
+
+
+LIGHT_AT = np.array([0.5, 1.0, 3.0])
+LIGHT_INSTANCE = "Instance {{ Data [${}] Transform [1 0 0 0  0 1 0 0  0 0 1 0  -0.5 -1.0 -3.0 1] }}"  # world -> local
+
+
+def test_direct_light_from_a_distant_disk_is_the_analytic_value():
+    """Direct lighting has a closed form on a Lambert floor under a black sky, and nothing in the reference tests it:
+    DistantDiskLight (distant_disk_light.rs:59-85) delivers irradiance `colour` at normal incidence whatever its radius
+    (radiance colour / solid angle, pdf 1 / solid angle), so every sample is albedo / pi * colour * cos(theta).  Pins the
+    world-light selection, the cone sampling and its pdf, Lambert evaluation and the MIS weight's limit."""
+    _, samp, _ = _lit_floor(world_light="DistantDiskLight $sun { Direction [-0.3 0.4 -0.8] Color [rec709, 2 2 2] Radius [0.001] }")
+    want = 2.0 * 0.6 / np.pi * 0.8 / np.sqrt(0.09 + 0.16 + 0.64)
+    assert np.abs(samp / want - 1.0).max() < 2e-3, (samp.min(), samp.max(), want)
+
+
+def test_direct_light_from_a_rectangle_is_the_analytic_value():
+    """RectangleLight (rectangle_light.rs:121-243): radiance colour / area * 0.5 (the power is shared by the two
+    sides, :191), sampled uniformly over the solid angle of its two spherical triangles.  The pixel means must
+    integrate to albedo / pi * E with E the irradiance of that rectangle, here by quadrature over its area."""
+    for w, h in ((0.4, 0.3), (2.0, 1.0)):
+        k = 30.0
+        pos, samp, spp = _lit_floor(objects=f"RectangleLight $panel {{ Color [rec709, {k} {k} {k}] Dimensions [{w} {h}] }}",
+                                    instances=LIGHT_INSTANCE.format("panel"))
+        g = (np.arange(24) + 0.5) / 24 - 0.5
+        qx, qy = np.meshgrid(g * w, g * h)
+        q = np.stack([LIGHT_AT[0] + qx.ravel(), LIGHT_AT[1] + qy.ravel(), np.full(qx.size, LIGHT_AT[2])], 1)
+        radiance = k / (w * h) * 0.5
+        e = np.zeros(len(pos))
+        for a in range(0, len(pos), 2048):
+            v = q[None, :, :] - pos[a:a + 2048, None, :]
+            d2 = (v ** 2).sum(2)
+            cos = v[:, :, 2] / np.sqrt(d2)     # the same at the floor and at the light: both are horizontal
+            e[a:a + 2048] = (radiance * cos * cos / d2).mean(1) * (w * h)
+        want = 0.6 / np.pi * e
+        got = samp[:, 0]
+        assert (got > 0).all()
+        assert abs(got.mean() / want.mean() - 1.0) < 3e-3
+        per_pixel = got.reshape(-1, spp).mean(1) / want.reshape(-1, spp).mean(1)
+        assert np.abs(per_pixel - 1.0).max() < 0.03
+
+
+def test_direct_light_from_a_sphere_and_the_references_skewed_basis():
+    """SphereLight (sphere_light.rs:85-192): radiance colour / (4 pi r^2), cone sampling, so a small sphere at distance d
+    gives E = colour * cos / (4 d^2) and the samples that reach it are exact.  But a seventh of them do not: the
+    reference hands the UN-normalised vector to the light's centre to coordinate_system_from_vector (:106-111), whose
+    construction (math.rs:26-34, Duff et al.) assumes unit length; the tangent axes come out skewed, grazing cone
+    samples land on the far side of the sphere, and their shadow rays are stopped by the light itself.  The oracle and
+    the CUDA path reproduce this: it is the reference's arithmetic, and parity is judged against it."""
+    k, r = 40.0, 0.05
+    pos, samp, _ = _lit_floor(objects=f"SphereLight $bulb {{ Color [rec709, {k} {k} {k}] Radius [{r}] }}",
+                              instances=LIGHT_INSTANCE.format("bulb"))
+    v = LIGHT_AT - pos
+    d2 = (v ** 2).sum(1)
+    want = 0.6 / np.pi * (k / (4 * np.pi * r * r)) * np.pi * r * r / d2 * (v[:, 2] / np.sqrt(d2))
+    ratio = samp[:, 0] / want
+    lost = ratio == 0.0
+    assert 0.08 < lost.mean() < 0.2, lost.mean()
+    assert abs(np.median(ratio[~lost]) - 1.0) < 2e-3
+    lo, hi = np.percentile(ratio[~lost], [1, 99])
+    assert 0.97 < lo and hi < 1.03, (lo, hi)
