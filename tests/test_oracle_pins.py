@@ -412,3 +412,79 @@ def test_direct_light_from_a_sphere_and_the_references_skewed_basis():
     assert abs(np.median(ratio[~lost]) - 1.0) < 2e-3
     lo, hi = np.percentile(ratio[~lost], [1, 99])
     assert 0.97 < lo and hi < 1.03, (lo, hi)
+
+
+def _rect_irradiance(pos, centre, ex, ey, w, h, radiance, n=24):
+    """Irradiance on the floor (normal +z) at `pos` from a two-sided rectangle, by midpoint quadrature over its area."""
+    g = (np.arange(n) + 0.5) / n - 0.5
+    qx, qy = np.meshgrid(g * w, g * h)
+    q = centre[None, :] + qx.ravel()[:, None] * ex[None, :] + qy.ravel()[:, None] * ey[None, :]
+    nl = np.cross(ex, ey)
+    e = np.zeros(len(pos))
+    for a in range(0, len(pos), 2048):
+        v = q[None, :, :] - pos[a:a + 2048, None, :]
+        d2 = (v ** 2).sum(2)
+        dist = np.sqrt(d2)
+        e[a:a + 2048] = (radiance * np.clip(v[:, :, 2] / dist, 0, None) * np.abs((v * nl).sum(2)) / dist / d2).mean(1) * (w * h)
+    return e
+
+
+def test_light_tree_selection_is_divided_out():
+    """Two rectangle lights of very different power and distance: the floor must receive the SUM of their analytic
+    contributions — LightTree::select's probabilities (light_tree.rs:135-201) are importance estimates and must cancel."""
+    lights = [dict(c=np.array([0.5, 1.0, 3.0]), w=0.4, h=0.3, k=30.0), dict(c=np.array([-2.0, 4.0, 2.0]), w=1.0, h=0.5, k=4.0)]
+    objs = "".join(f"RectangleLight $p{i} {{ Color [rec709, {l['k']} {l['k']} {l['k']}] Dimensions [{l['w']} {l['h']}] }}\n"
+                   for i, l in enumerate(lights))
+    insts = "".join(f"Instance {{ Data [$p{i}] Transform [1 0 0 0  0 1 0 0  0 0 1 0  {-l['c'][0]} {-l['c'][1]} {-l['c'][2]} 1] }}\n"
+                    for i, l in enumerate(lights))
+    pos, samp, spp = _lit_floor(objects=objs, instances=insts, spp=64)
+    ex, ey = np.array([1.0, 0, 0]), np.array([0, 1.0, 0])
+    e = sum(_rect_irradiance(pos, l["c"], ex, ey, l["w"], l["h"], l["k"] / (l["w"] * l["h"]) * 0.5) for l in lights)
+    want, got = 0.6 / np.pi * e, samp[:, 0]
+    assert abs(got.mean() / want.mean() - 1.0) < 4e-3
+    per_pixel = got.reshape(-1, spp).mean(1) / want.reshape(-1, spp).mean(1)
+    assert np.abs(per_pixel - 1.0).max() < 0.05
+
+
+def test_light_inside_a_rotated_sub_assembly():
+    """Assembly::sample_lights (assembly.rs:46-140) takes the shading point into the instance's space and the light
+    sample back out: a rectangle light inside a sub-assembly that is instanced with a rotation and a translation must
+    light the floor like the same rectangle placed there directly."""
+    a = np.radians(40.0)
+    rot = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    shift, local = np.array([1.0, 2.0, 0.5]), np.array([0.3, -0.2, 2.5])
+    cols = [rot.T[:, 0], rot.T[:, 1], rot.T[:, 2], -rot.T @ shift]  # world -> local, column-major, fourth row dropped
+    xf = " ".join(f"{v:.9g}" for j, col in enumerate(cols) for v in list(col) + [1.0 if j == 3 else 0.0])
+    w, h, k = 0.6, 0.4, 25.0
+    objs = f"""Assembly $sub {{
+            RectangleLight $panel {{ Color [rec709, {k} {k} {k}] Dimensions [{w} {h}] }}
+            Instance {{ Data [$panel] Transform [1 0 0 0  0 1 0 0  0 0 1 0  {-local[0]} {-local[1]} {-local[2]} 1] }}
+        }}"""
+    pos, samp, spp = _lit_floor(objects=objs, instances=f"Instance {{ Data [$sub] Transform [{xf}] }}", spp=32)
+    e = _rect_irradiance(pos, rot @ local + shift, rot @ np.array([1.0, 0, 0]), rot @ np.array([0, 1.0, 0]), w, h,
+                         k / (w * h) * 0.5)
+    want, got = 0.6 / np.pi * e, samp[:, 0]
+    assert abs(got.mean() / want.mean() - 1.0) < 4e-3
+    per_pixel = got.reshape(-1, spp).mean(1) / want.reshape(-1, spp).mean(1)
+    assert np.abs(per_pixel - 1.0).max() < 0.04
+
+
+def test_lights_seen_directly_and_the_references_factor_of_two():
+    """A camera ray that hits a light picks up its Emit closure: colour / (4 pi r^2) for a sphere
+    (sphere_light.rs:318-323) — the radiance its sampling uses — and colour / area for a rectangle
+    (rectangle_light.rs:316-320), which is TWICE the colour / area * 0.5 its sampling uses (:191).  The reference is
+    inconsistent there (a floor close under a large rectangle light comes out brighter than either convention alone);
+    both sides of the parity reproduce it."""
+    from psychopath_b200 import api
+    from scenes import lit_floor_text
+    for obj, name, want, kind in (("RectangleLight $l { Color [rec709, 10 10 10] Dimensions [3.0 2.0] }", "l", 10.0 / 6.0, abi.HIT_RECT_LIGHT),
+                                  ("SphereLight $l { Color [rec709, 10 10 10] Radius [0.8] }", "l", 10.0 / (4 * np.pi * 0.64), abi.HIT_SPHERE_LIGHT)):
+        text = lit_floor_text(objects=obj, instances="Instance { Data [$l] Transform [1 0 0 0  0 1 0 0  0 0 1 0  -0.5 -1.0 -0.9 1] }", spp=4)
+        s = api.Scene.from_psy_string(text)
+        d = s.desc.contents
+        rays = O.camera_rays(s.desc, 0, 0, d.res_x, d.res_y, d.spp, d.seed)
+        hits, _, _ = O.trace_rays(s.desc, rays)
+        _, samp, _ = O.render_bucket(s.desc, 0, 0, d.res_x, d.res_y, d.spp, d.seed, want_samples=True)
+        direct = hits["kind"] == kind
+        assert direct.mean() > 0.05
+        assert np.abs(samp.reshape(-1, 4)[direct] / want - 1.0).max() < 1e-3
