@@ -373,6 +373,15 @@ def edge_case_texts():
     }
     cases["white_furnace_motion_dof"] = furnace_text("Type [Lambert] Color [rec709, 1 1 1]", motion=True, aperture=0.2)
     cases["ggx_furnace"] = furnace_text("Type [GGX] Color [rec709, 1 1 1] Roughness [0.4] Fresnel [1.0]")
+    # the closed-form direct-lighting scenes of tests/test_oracle_pins.py
+    at = "Transform [1 0 0 0  0 1 0 0  0 0 1 0  -0.5 -1.0 -3.0 1]"
+    cases["floor_under_a_distant_disk"] = lit_floor_text(
+        world_light="DistantDiskLight $sun { Direction [-0.3 0.4 -0.8] Color [rec709, 2 2 2] Radius [0.001] }", spp=4)
+    cases["floor_under_a_sphere_light"] = lit_floor_text(
+        objects="SphereLight $bulb { Color [rec709, 40 40 40] Radius [0.05] }", instances=f"Instance {{ Data [$bulb] {at} }}", spp=4)
+    cases["floor_under_a_large_close_rectangle"] = lit_floor_text(
+        objects="RectangleLight $l { Color [rec709, 10 10 10] Dimensions [3.0 2.0] }",
+        instances="Instance { Data [$l] Transform [1 0 0 0  0 1 0 0  0 0 1 0  -0.5 -1.0 -0.9 1] }", spp=4)
     return cases
 
 
