@@ -488,3 +488,38 @@ def test_lights_seen_directly_and_the_references_factor_of_two():
         direct = hits["kind"] == kind
         assert direct.mean() > 0.05
         assert np.abs(samp.reshape(-1, 4)[direct] / want - 1.0).max() < 1e-3
+
+
+def test_camera_rays_are_the_pinhole_and_thin_lens_projection():
+    """Camera::generate_ray and the image-plane mapping (camera.rs:74-102, renderer.rs:214-255) in closed form: with a
+    closed aperture every ray leaves the camera position and, in camera space, dir.xy / dir.z of a pixel's samples
+    averages to the pixel centre on the plane z = 1 (x in [-tan(fov/2), tan(fov/2)], y scaled by H / W, row 0 at the
+    top); with an open aperture all rays of a pixel sample still cross at the pixel's point on the focus plane."""
+    from psychopath_b200 import api
+    from scenes import lit_floor_text
+    w, h, spp = 32, 24, 64
+    for aperture in (0.0, 0.3):
+        text = lit_floor_text(res=(w, h), spp=spp).replace("ApertureRadius [0.0]", f"ApertureRadius [{aperture}]")
+        s = api.Scene.from_psy_string(text)
+        rays = O.camera_rays(s.desc, 0, 0, w, h, spp, 5)
+        # the fixture's camera: world <- camera columns X = (1,0,0), Y = (0,0.6,0.8), Z = (0,0.8,-0.6), at (0,-6,5)
+        m = np.array([[1, 0, 0], [0, 0.6, 0.8], [0, 0.8, -0.6]], dtype=np.float64).T   # columns X Y Z
+        o = (rays["orig"].astype(np.float64) - np.array([0, -6.0, 5.0])) @ m           # camera-space origin
+        d = rays["dir"].astype(np.float64) @ m
+        assert (d[:, 2] > 0).all()
+        tfov = np.tan(np.radians(35.0) / 2)
+        focus = 9.0
+        # where each ray crosses the focus plane z = focus (z = 1 for the pinhole), as image-plane coordinates
+        t = ((focus if aperture else 1.0) - o[:, 2]) / d[:, 2]
+        p = (o + d * t[:, None])[:, :2] / ((focus if aperture else 1.0) * tfov)
+        p = p.reshape(h, w, spp, 2)
+        px = ((np.arange(w) + 0.5) / w - 0.5) * 2.0
+        py = (0.5 - (np.arange(h) + 0.5) / h) * 2.0 * (h / w)
+        assert np.abs(p[..., 0].mean(2) - px[None, :]).max() < 0.25 * 2.0 / w      # pixel centre, within a quarter pixel
+        assert np.abs(p[..., 1].mean(2) - py[:, None]).max() < 0.25 * 2.0 / w
+        assert np.abs(p[..., 0] - px[None, :, None]).max() < 2.5 * 2.0 / w          # the filter's footprint: a few pixels
+        if aperture == 0.0:
+            assert np.abs(o).max() < 1e-5
+        else:
+            r = np.hypot(o[:, 0], o[:, 1])
+            assert np.abs(o[:, 2]).max() < 1e-5 and r.max() <= aperture * 1.0001 and r.max() > 0.9 * aperture
