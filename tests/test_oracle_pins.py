@@ -523,3 +523,38 @@ def test_camera_rays_are_the_pinhole_and_thin_lens_projection():
         else:
             r = np.hypot(o[:, 0], o[:, 1])
             assert np.abs(o[:, 2]).max() < 1e-5 and r.max() <= aperture * 1.0001 and r.max() > 0.9 * aperture
+
+
+def test_sphere_lambert_against_quadrature():
+    """The light tree's importance estimate for Lambert surfaces (surface_closure.rs:351-377, Snyder's clamped-cosine
+    integral over a spherical cap) against a direct quadrature of max(cos, 0) / pi over the cap: exact where the cap is
+    wholly above the horizon and where its centre is below it.  In between the reference writes
+    `nlcos * rsin2 + g - h` where Snyder's formula has `(g - h) / pi`; the oracle (and the CUDA path) keep the
+    reference's expression — it only steers which light a path picks, the pick's probability is divided out again
+    (test_light_tree_selection_is_divided_out)."""
+    lib = O.load()
+    lib.oracle_sphere_lambert.restype = C.c_float
+    lib.oracle_sphere_lambert.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_float)]
+    out = (C.c_float * 4)()
+
+    def quadrature(nl, r, n=1200):
+        th = (np.arange(n) + 0.5) / n * r
+        ph = (np.arange(n) + 0.5) / n * 2 * np.pi
+        t, p = np.meshgrid(th, ph, indexing="ij")
+        z = -np.sin(t) * np.cos(p) * np.sin(nl) + np.cos(t) * np.cos(nl)   # cap around an axis at angle nl from the normal
+        return (np.clip(z, 0, None) * np.sin(t)).sum() * (r / n) * (2 * np.pi / n) / np.pi
+
+    def f(nl, r):
+        return lib.oracle_sphere_lambert(np.float32(np.cos(nl)), np.float32(np.cos(r)), out)
+
+    for nl, r in ((0.3, 0.2), (1.0, 0.4), (0.0, 1.2), (0.9, 0.6)):       # wholly above the horizon
+        assert abs(f(nl, r) / quadrature(nl, r) - 1.0) < 1e-5
+        assert abs(f(nl, r) / (np.cos(nl) * np.sin(r) ** 2) - 1.0) < 1e-5
+    for nl, r in ((1.7, 0.4), (2.0, 0.6), (1.6, 1.0)):                   # centre below the horizon, cap still reaching above
+        assert abs(f(nl, r) / quadrature(nl, r) - 1.0) < 1e-4
+    assert f(2.2, 0.5) == 0.0                                               # wholly below
+    for nl, r in ((1.4, 0.3), (1.5, 0.5), (1.2, 0.7)):                   # straddling, centre above: the reference's form
+        got, exact = f(nl, r), quadrature(nl, r)
+        flat = np.cos(nl) * np.sin(r) ** 2
+        assert abs((flat + (got - flat) / np.pi) / exact - 1.0) < 1e-4      # Snyder's value once (g - h) is divided by pi
+        assert got > exact                                                  # as written, an over-estimate
