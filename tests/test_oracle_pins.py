@@ -558,3 +558,34 @@ def test_sphere_lambert_against_quadrature():
         flat = np.cos(nl) * np.sin(r) ** 2
         assert abs((flat + (got - flat) / np.pi) / exact - 1.0) < 1e-4      # Snyder's value once (g - h) is divided by pi
         assert got > exact                                                  # as written, an over-estimate
+
+
+def test_fast_exp_and_plancks_law_in_closed_form():
+    """`fastapprox::fast::exp` is an un-vendored dependency restated from its published algorithm (SURVEY.md 8c): its
+    error against exp() must be the library's (a few 1e-5 relative; a wrong constant shows up as 1e-2 or worse).
+    Blackbody colours (color.rs:336-383) follow Planck's law in W sr^-1 m^-2 um^-1... times 1e-6, at the hero wavelength
+    and three more a quarter of the range apart, zero below 200 K; Temperature colours are that times 4e7 / T^4."""
+    lib = O.load()
+    lib.oracle_fast_exp.restype = C.c_float
+    lib.oracle_fast_exp.argtypes = [C.c_float]
+    xs = np.linspace(-80, 80, 4001).astype(np.float32)
+    rel = np.array([lib.oracle_fast_exp(x) / np.exp(np.float64(x)) - 1.0 for x in xs])
+    assert np.abs(rel).max() < 1e-4, np.abs(rel).max()
+
+    def planck(t, wl_nm):
+        c, h, kb = 299792458.0, 6.62607015e-34, 1.38064852e-23
+        wl = wl_nm * 1e-9
+        return 2 * h * c * c / wl ** 5 / (np.exp(h * c / (wl * kb * t)) - 1.0) * 1e-6
+
+    e = (C.c_float * 4)()
+    for t in (1000.0, 2500.0, 3200.0, 5600.0, 6500.0, 9000.0, 15000.0):
+        for hero in (380.0, 455.0, 530.0, 612.0, 699.0):
+            wls = [380.0 + (hero - 380.0 + 80.0 * i) % 320.0 for i in range(4)]
+            lib.oracle_color_to_spectral(C.byref(abi.PsyColor(1, t, 2.5, 0.0)), C.c_float(hero), e)
+            for i in range(4):
+                assert abs(e[i] / (2.5 * planck(t, wls[i])) - 1.0) < 1.5e-4, (t, hero, i)
+            lib.oracle_color_to_spectral(C.byref(abi.PsyColor(2, t, 2.5, 0.0)), C.c_float(hero), e)
+            for i in range(4):
+                assert abs(e[i] / (2.5 * planck(t, wls[i]) * 4.0e7 / t ** 4) - 1.0) < 1.5e-4
+    lib.oracle_color_to_spectral(C.byref(abi.PsyColor(1, 150.0, 1.0, 0.0)), C.c_float(500.0), e)
+    assert list(e) == [0.0, 0.0, 0.0, 0.0]
