@@ -589,3 +589,17 @@ def test_fast_exp_and_plancks_law_in_closed_form():
                 assert abs(e[i] / (2.5 * planck(t, wls[i]) * 4.0e7 / t ** 4) - 1.0) < 1.5e-4
     lib.oracle_color_to_spectral(C.byref(abi.PsyColor(1, 150.0, 1.0, 0.0)), C.c_float(500.0), e)
     assert list(e) == [0.0, 0.0, 0.0, 0.0]
+
+
+def test_power_heuristic_is_the_pdf_over_the_mis_weight():
+    """mis.rs:12-21 returns a / (a^2 / (a^2 + b^2)), the pdf divided by the power-heuristic weight (so dividing a
+    contribution by it applies the weight and the pdf at once), and passes an infinite a through (delta lights)."""
+    lib = O.load()
+    f = lib.oracle_power_heuristic
+    for a, b in ((1.0, 1.0), (3.0, 0.5), (0.25, 8.0), (1146.0, 0.3), (2.0, 0.0)):
+        w = a * a / (a * a + b * b)
+        assert abs(f(a, b) / (a / w) - 1.0) < 1e-6
+    assert f(float("inf"), 3.0) == float("inf")
+    # the two weights of a pair of techniques add up to one
+    for a, b in ((1.0, 1.0), (3.0, 0.5), (0.25, 8.0)):
+        assert abs(a / f(a, b) + b / f(b, a) - 1.0) < 1e-6
