@@ -428,3 +428,38 @@ Scene $nee {{
     }}
 }}
 """
+
+
+def deeply_nested_text(levels):
+    """`levels` assemblies inside one another below the root, each instanced twice with a small transform (one of them
+    moving), a box and a lamp at the bottom: the nesting limit of the trace kernels' saved-space stack."""
+    inner = """SurfaceShader $s { Type [Lambert] Color [rec709, 0.7 0.5 0.3] }
+            MeshSurface $box {
+                Vertices [-0.5 -0.5 0  0.5 -0.5 0  0.5 0.5 0  -0.5 0.5 0  -0.5 -0.5 1  0.5 -0.5 1  0.5 0.5 1  -0.5 0.5 1]
+                FaceVertCounts [4 4 4 4 4 4]
+                FaceVertIndices [0 3 2 1  4 5 6 7  0 1 5 4  1 2 6 5  2 3 7 6  3 0 4 7]
+            }
+            SphereLight $lamp { Color [rec709, 8 7 6] Radius [0.1] }
+            Instance { Data [$box] SurfaceShaderBind [$s] }
+            Instance { Data [$lamp] Transform [1 0 0 0  0 1 0 0  0 0 1 0  0.2 0.9 -1.6 1] }"""
+    body = inner
+    for k in range(levels, 0, -1):
+        body = f"""Assembly $a{k} {{
+            {body}
+        }}
+        Instance {{ Data [$a{k}] Transform [0.98 0.17 0 0  -0.17 0.98 0 0  0 0 1 0  0.35 0.1 0 1] }}
+        Instance {{ Data [$a{k}] Transform [1 0 0 0  0 1 0 0  0 0 1 0  -0.9 -0.3 0 1] Transform [1 0 0 0  0 1 0 0  0 0 1 0  -1.0 -0.3 -0.05 1] }}"""
+    return f"""
+Scene $deep {{
+    Output {{ Path ["deep.png"] }}
+    RenderSettings {{ Resolution [48 32] SamplesPerPixel [4] Seed [2] }}
+    Camera {{ Fov [55.0] FocalDistance [9.0] ApertureRadius [0.0] Transform [1 0 0 0  0 0 1 0  0 1 0 0  0 -14 1 1] }}
+    World {{ BackgroundShader {{ Type [Color] Color [rec709, 0.1 0.1 0.12] }} }}
+    Assembly {{
+        SurfaceShader $g {{ Type [Lambert] Color [rec709, 0.5 0.5 0.5] }}
+        MeshSurface $floor {{ Vertices [-20 -20 0  20 -20 0  20 20 0  -20 20 0] FaceVertCounts [4] FaceVertIndices [0 1 2 3] }}
+        Instance {{ Data [$floor] SurfaceShaderBind [$g] }}
+        {body}
+    }}
+}}
+"""

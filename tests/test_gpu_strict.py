@@ -144,3 +144,21 @@ def test_edge_scenes_bit_exact(name):
     pimg, _ = api.Renderer(scene).render()
     assert np.isfinite(pimg).all()
     assert np.linalg.norm(pimg - oimg) / np.linalg.norm(oimg) <= 2e-3
+
+
+def test_nesting_up_to_the_limit_is_bit_exact_and_beyond_it_fails_loudly():
+    """Seven assemblies inside one another below the root (2^7 moving instance paths of a box and a lamp) render with
+    the oracle's bits; eight exceed the trace kernels' saved-space stack (TRACE_MAX_NEST) and the upload refuses the
+    scene with PSY_ERR_LIMIT instead of rendering something else."""
+    from scenes import deeply_nested_text
+    scene = api.Scene.from_psy_string(deeply_nested_text(7))
+    d = scene.desc.contents
+    r = api.Renderer(scene, strict=True)
+    gs, st = r.render_bucket_samples(0, 0, d.res_x, d.res_y, d.spp, d.seed)
+    with O.strict_math():
+        _, osamp, ost = O.render_bucket(scene.desc, 0, 0, d.res_x, d.res_y, d.spp, d.seed, want_samples=True)
+    assert st["ray_count"] == ost.ray_count
+    assert same_or_both_nan(gs, osamp).all()
+    too_deep = api.Scene.from_psy_string(deeply_nested_text(8))
+    with pytest.raises(api.PsyError, match="nesting"):
+        api.Renderer(too_deep)
